@@ -1,0 +1,650 @@
+// fastsmc_b200 — implementation of the C ABI declared in include/fastsmc_b200.h.
+// Host side of the decode path: device buffers, model assembly, tile scheduling, launches.
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <string>
+#include <vector>
+
+#include "decode_kernels.cuh"
+
+namespace
+{
+
+thread_local std::string gLastError;
+
+int fail(const int code, const char* fmt, ...)
+{
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof buf, fmt, ap);
+  va_end(ap);
+  gLastError = buf;
+  return code;
+}
+
+#define FSMC_CUDA(expr)                                                                                  \
+  do {                                                                                                   \
+    const cudaError_t e_ = (expr);                                                                       \
+    if (e_ != cudaSuccess) {                                                                             \
+      return fail(e_ == cudaErrorMemoryAllocation ? FSMC_E_NOMEM : FSMC_E_CUDA, "%s failed: %s (%s:%d)", \
+                  #expr, cudaGetErrorString(e_), __FILE__, __LINE__);                                    \
+    }                                                                                                    \
+  } while (0)
+
+template <class T> struct DevBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~DevBuf() { release(); }
+  void release()
+  {
+    if (p) {
+      cudaFree(p);
+      p = nullptr;
+      n = 0;
+    }
+  }
+  cudaError_t ensure(const size_t count)
+  {
+    if (count <= n && p) {
+      return cudaSuccess;
+    }
+    release();
+    const cudaError_t e = cudaMalloc(&p, std::max<size_t>(count, 1) * sizeof(T));
+    if (e == cudaSuccess) {
+      n = count;
+    }
+    return e;
+  }
+};
+
+}  // namespace
+
+struct fsmc_ctx {
+  int device = 0;
+  cudaStream_t ownStream = nullptr;
+  cudaStream_t stream = nullptr;
+  cudaDeviceProp prop{};
+  bool hasModel = false, hasHaps = false;
+  fsmc::DeviceModel model{};
+  DevBuf<float> siteRows, prior, expTimes, colRatios;
+  DevBuf<uint64_t> haps;
+  long long numHaps = 0;
+  DevBuf<float> scratch;
+  cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+struct fsmc_plan {
+  long long numTiles = 0;
+  unsigned flags = 0;
+  long long maxLen = 0;
+  double pairSites = 0.0;
+  long long segmentCapacity = 0;
+  long long siteStride = 0;
+  DevBuf<uint32_t> hapA, hapB;
+  DevBuf<int> tilePairs, tileFrom, tileTo, scanFrom, scanTo, order;
+  DevBuf<fsmc_segment> segments;
+  DevBuf<unsigned long long> counters;  // [0] segment count, [1] tile queue head
+  DevBuf<float> siteMean, siteIbd;
+  DevBuf<int> siteMap;
+  // launch geometry
+  int statesKernel = 0;
+  int mode = 2;
+  int threads = 128;
+  int blocks = 0;
+  size_t smemBytes = 0;
+  long long scratchPerWarp = 0;
+  bool launched = false;
+  int launches = 0;
+};
+
+namespace
+{
+
+using fsmc::DecodeArgs;
+using fsmc::DeviceModel;
+
+typedef void (*KernelFn)(const DeviceModel, const DecodeArgs);
+
+struct KernelChoice {
+  KernelFn fn;
+  int statesKernel;
+  int mode;
+  int threads;
+};
+
+// Specialisations: the state counts of the decoding-quantity files shipped with the reference
+// (69 = 30-100-2000 / UKBB, 159 = FASTSMC_EXAMPLE) get register-resident kernels; anything else
+// runs on the generic shared-memory kernel.
+KernelChoice chooseKernel(const int S, const unsigned flags)
+{
+  const bool exact = flags & FSMC_EXACT;
+  const bool generic = flags & FSMC_GENERIC_KERNEL;
+  if (!generic && S == 69) {
+    return exact ? KernelChoice{fsmc::decodeTilesKernel<69, 0, true, 128, 2>, 69, 0, 128}
+                 : KernelChoice{fsmc::decodeTilesKernel<69, 0, false, 128, 2>, 69, 0, 128};
+  }
+  if (!generic && S == 159) {
+    return exact ? KernelChoice{fsmc::decodeTilesKernel<159, 1, true, 128, 1>, 159, 1, 128}
+                 : KernelChoice{fsmc::decodeTilesKernel<159, 1, false, 128, 1>, 159, 1, 128};
+  }
+  return exact ? KernelChoice{fsmc::decodeTilesKernel<0, 2, true, 128, 1>, 0, 2, 128}
+               : KernelChoice{fsmc::decodeTilesKernel<0, 2, false, 128, 1>, 0, 2, 128};
+}
+
+size_t smemPerWarp(const DeviceModel& m, const int mode, const unsigned flags)
+{
+  const bool age = (flags & FSMC_SEG_AGE) && (flags & FSMC_CALL_SEGMENTS);
+  const size_t rows = (age ? m.ageThreshold : 0) + (mode >= 1 ? m.S : 0) + (mode == 2 ? m.S : 0);
+  return rows * 32 * sizeof(float);
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* fsmc_last_error(void)
+{
+  return gLastError.c_str();
+}
+
+int fsmc_version(void)
+{
+  return 100;
+}
+
+int fsmc_device_count(void)
+{
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) {
+    cudaGetLastError();
+    return 0;
+  }
+  return n;
+}
+
+int fsmc_ctx_create(const int device, fsmc_ctx** out)
+{
+  if (!out) {
+    return fail(FSMC_E_INVALID, "fsmc_ctx_create: out is NULL");
+  }
+  *out = nullptr;
+  int n = 0;
+  FSMC_CUDA(cudaGetDeviceCount(&n));
+  if (device < 0 || device >= n) {
+    return fail(FSMC_E_INVALID, "fsmc_ctx_create: device %d out of range (%d visible)", device, n);
+  }
+  FSMC_CUDA(cudaSetDevice(device));
+  auto* ctx = new fsmc_ctx;
+  ctx->device = device;
+  cudaError_t e = cudaGetDeviceProperties(&ctx->prop, device);
+  if (e == cudaSuccess) {
+    e = cudaStreamCreateWithFlags(&ctx->ownStream, cudaStreamNonBlocking);
+  }
+  for (int i = 0; i < 4 && e == cudaSuccess; ++i) {
+    e = cudaEventCreate(&ctx->ev[i]);
+  }
+  if (e != cudaSuccess) {
+    delete ctx;
+    return fail(FSMC_E_CUDA, "fsmc_ctx_create: %s", cudaGetErrorString(e));
+  }
+  ctx->stream = ctx->ownStream;
+  *out = ctx;
+  return FSMC_OK;
+}
+
+int fsmc_ctx_destroy(fsmc_ctx* ctx)
+{
+  if (!ctx) {
+    return FSMC_OK;
+  }
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (auto& e : ctx->ev) {
+    if (e) {
+      cudaEventDestroy(e);
+    }
+  }
+  if (ctx->ownStream) {
+    cudaStreamDestroy(ctx->ownStream);
+  }
+  delete ctx;
+  return FSMC_OK;
+}
+
+int fsmc_ctx_set_stream(fsmc_ctx* ctx, void* cuda_stream)
+{
+  if (!ctx) {
+    return fail(FSMC_E_INVALID, "fsmc_ctx_set_stream: ctx is NULL");
+  }
+  ctx->stream = cuda_stream ? static_cast<cudaStream_t>(cuda_stream) : ctx->ownStream;
+  return FSMC_OK;
+}
+
+int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
+{
+  if (!ctx || !mdl) {
+    return fail(FSMC_E_INVALID, "fsmc_set_model: NULL argument");
+  }
+  const int S = mdl->states, L = mdl->sites;
+  if (S < 2 || L < 1 || mdl->numDistances < 1 || !mdl->initialStateProb || !mdl->expectedTimes ||
+      !mdl->columnRatios || !mdl->emission1 || !mdl->emission0minus1 || !mdl->emission2minus0 || !mdl->D ||
+      !mdl->B || !mdl->U || !mdl->RR || !mdl->distanceRow) {
+    return fail(FSMC_E_INVALID, "fsmc_set_model: bad sizes or NULL table (states=%d sites=%d)", S, L);
+  }
+  if (mdl->stateThreshold < 0 || mdl->stateThreshold > S || mdl->ageThreshold < 0 || mdl->ageThreshold > S) {
+    return fail(FSMC_E_INVALID, "fsmc_set_model: thresholds out of range");
+  }
+  for (int s = 1; s < L; ++s) {
+    if (mdl->distanceRow[s] < 0 || mdl->distanceRow[s] >= mdl->numDistances) {
+      return fail(FSMC_E_INVALID, "fsmc_set_model: distanceRow[%d]=%d out of range", s, mdl->distanceRow[s]);
+    }
+  }
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  const int Spad = (S + 3) / 4 * 4;
+  cudaStream_t st = ctx->stream;
+
+  // staging copies of the caller's tables, gathered into per-site rows on the device
+  DevBuf<float> e1, e0, e2, D, B, U, R;
+  DevBuf<int> rowIdx;
+  const size_t nE = static_cast<size_t>(L) * S, nT = static_cast<size_t>(mdl->numDistances) * S;
+  FSMC_CUDA(e1.ensure(nE));
+  FSMC_CUDA(e0.ensure(nE));
+  FSMC_CUDA(e2.ensure(nE));
+  FSMC_CUDA(D.ensure(nT));
+  FSMC_CUDA(B.ensure(nT));
+  FSMC_CUDA(U.ensure(nT));
+  FSMC_CUDA(R.ensure(nT));
+  FSMC_CUDA(rowIdx.ensure(L));
+  FSMC_CUDA(ctx->siteRows.ensure(static_cast<size_t>(L) * fsmc::kRowArrays * Spad));
+  FSMC_CUDA(ctx->prior.ensure(Spad));
+  FSMC_CUDA(ctx->expTimes.ensure(Spad));
+  FSMC_CUDA(ctx->colRatios.ensure(Spad));
+  FSMC_CUDA(cudaMemcpyAsync(e1.p, mdl->emission1, nE * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(e0.p, mdl->emission0minus1, nE * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(e2.p, mdl->emission2minus0, nE * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(D.p, mdl->D, nT * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(B.p, mdl->B, nT * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(U.p, mdl->U, nT * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(R.p, mdl->RR, nT * sizeof(float), cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(rowIdx.p, mdl->distanceRow, L * sizeof(int), cudaMemcpyHostToDevice, st));
+  std::vector<float> pad(Spad, 0.f);
+  auto upPad = [&](float* dst, const float* src) {
+    std::fill(pad.begin(), pad.end(), 0.f);
+    std::copy(src, src + S, pad.begin());
+    return cudaMemcpyAsync(dst, pad.data(), Spad * sizeof(float), cudaMemcpyHostToDevice, st);
+  };
+  FSMC_CUDA(upPad(ctx->prior.p, mdl->initialStateProb));
+  FSMC_CUDA(cudaStreamSynchronize(st));
+  FSMC_CUDA(upPad(ctx->expTimes.p, mdl->expectedTimes));
+  FSMC_CUDA(cudaStreamSynchronize(st));
+  FSMC_CUDA(upPad(ctx->colRatios.p, mdl->columnRatios));
+  FSMC_CUDA(cudaStreamSynchronize(st));
+
+  const int threads = 256;
+  const int blocks = std::max(1, ctx->prop.multiProcessorCount * 8);
+  fsmc::buildSiteRowsKernel<<<blocks, threads, 0, st>>>(S, Spad, L, e1.p, e0.p, e2.p, D.p, B.p, U.p, R.p, rowIdx.p,
+                                                         ctx->siteRows.p);
+  FSMC_CUDA(cudaGetLastError());
+  FSMC_CUDA(cudaStreamSynchronize(st));
+
+  DeviceModel& m = ctx->model;
+  m.S = S;
+  m.Spad = Spad;
+  m.L = L;
+  m.siteRows = ctx->siteRows.p;
+  m.prior = ctx->prior.p;
+  m.expTimes = ctx->expTimes.p;
+  m.colRatios = ctx->colRatios.p;
+  m.stateThreshold = mdl->stateThreshold;
+  m.ageThreshold = mdl->ageThreshold;
+  // the reference compares against `N * probabilityThreshold` with an int N promoted to float
+  m.thr[0] = 1000 * mdl->probabilityThreshold;
+  m.thr[1] = 100 * mdl->probabilityThreshold;
+  m.thr[2] = 10 * mdl->probabilityThreshold;
+  m.thr[3] = mdl->probabilityThreshold;
+  ctx->hasModel = true;
+  return FSMC_OK;
+}
+
+int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, const int64_t numHaps, const int64_t sites)
+{
+  if (!ctx || !bits || numHaps < 1 || sites < 1) {
+    return fail(FSMC_E_INVALID, "fsmc_set_haplotypes: bad argument");
+  }
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  const long long words = (sites + 63) / 64;
+  const size_t n = static_cast<size_t>(numHaps) * words;
+  FSMC_CUDA(ctx->haps.ensure(n));
+  FSMC_CUDA(cudaMemcpyAsync(ctx->haps.p, bits, n * sizeof(uint64_t), cudaMemcpyHostToDevice, ctx->stream));
+  FSMC_CUDA(cudaStreamSynchronize(ctx->stream));
+  ctx->model.haps = ctx->haps.p;
+  ctx->model.wordsPerHap = words;
+  ctx->numHaps = numHaps;
+  ctx->hasHaps = true;
+  return FSMC_OK;
+}
+
+int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** out)
+{
+  if (!ctx || !req || !out) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: NULL argument");
+  }
+  *out = nullptr;
+  if (!ctx->hasModel || !ctx->hasHaps) {
+    return fail(FSMC_E_STATE, "fsmc_plan_create: set the model and the haplotypes first");
+  }
+  const long long T = req->numTiles;
+  if (T < 0 || T > (1ll << 26)) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: numTiles=%lld out of range", T);
+  }
+  const unsigned flags = req->flags;
+  const bool seg = flags & FSMC_CALL_SEGMENTS;
+  const bool siteOut = flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP | FSMC_SITE_IBD);
+  if (T > 0 && (!req->hapA || !req->hapB || !req->tilePairs || !req->tileFrom || !req->tileTo ||
+                (seg && (!req->tileScanFrom || !req->tileScanTo)))) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: NULL input array");
+  }
+  const DeviceModel& m = ctx->model;
+  long long maxLen = 0;
+  double pairSites = 0.0;
+  for (long long t = 0; t < T; ++t) {
+    const int n = req->tilePairs[t], f = req->tileFrom[t], e = req->tileTo[t];
+    if (n < 1 || n > FSMC_TILE || f < 0 || e > m.L || e <= f) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_create: tile %lld has pairs=%d window=[%d,%d) (sites=%d)", t, n, f, e,
+                  m.L);
+    }
+    if (seg && (req->tileScanFrom[t] < f || req->tileScanTo[t] > e)) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_create: tile %lld scan window [%d,%d) outside decode window [%d,%d)", t,
+                  req->tileScanFrom[t], req->tileScanTo[t], f, e);
+    }
+    for (int l = 0; l < n; ++l) {
+      if (req->hapA[t * 32 + l] >= ctx->numHaps || req->hapB[t * 32 + l] >= ctx->numHaps) {
+        return fail(FSMC_E_INVALID, "fsmc_plan_create: tile %lld lane %d haplotype index out of range", t, l);
+      }
+    }
+    maxLen = std::max<long long>(maxLen, e - f);
+    pairSites += static_cast<double>(n) * (e - f);
+  }
+  if (siteOut && req->siteStride < maxLen) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: siteStride=%lld < longest window %lld",
+                static_cast<long long>(req->siteStride), maxLen);
+  }
+  if (seg && req->segmentCapacity < 0) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: negative segmentCapacity");
+  }
+
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  auto* plan = new fsmc_plan;
+  struct Guard {
+    fsmc_plan*& p;
+    bool keep = false;
+    ~Guard()
+    {
+      if (!keep) {
+        delete p;
+        p = nullptr;
+      }
+    }
+  } guard{plan};
+
+  plan->numTiles = T;
+  plan->flags = flags;
+  plan->maxLen = maxLen;
+  plan->pairSites = pairSites;
+  plan->segmentCapacity = seg ? req->segmentCapacity : 0;
+  plan->siteStride = siteOut ? req->siteStride : 0;
+
+  // longest-window-first launch order (dynamic queue → LPT schedule); stable, so equal windows keep input order
+  std::vector<int> order(T);
+  std::iota(order.begin(), order.end(), 0);
+  std::stable_sort(order.begin(), order.end(), [&](const int x, const int y) {
+    return (req->tileTo[x] - req->tileFrom[x]) > (req->tileTo[y] - req->tileFrom[y]);
+  });
+
+  cudaStream_t st = ctx->stream;
+  const size_t nLane = static_cast<size_t>(T) * 32;
+  FSMC_CUDA(plan->hapA.ensure(nLane));
+  FSMC_CUDA(plan->hapB.ensure(nLane));
+  FSMC_CUDA(plan->tilePairs.ensure(T));
+  FSMC_CUDA(plan->tileFrom.ensure(T));
+  FSMC_CUDA(plan->tileTo.ensure(T));
+  FSMC_CUDA(plan->order.ensure(T));
+  FSMC_CUDA(plan->counters.ensure(2));
+  if (T > 0) {
+    FSMC_CUDA(cudaMemcpyAsync(plan->hapA.p, req->hapA, nLane * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaMemcpyAsync(plan->hapB.p, req->hapB, nLane * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaMemcpyAsync(plan->tilePairs.p, req->tilePairs, T * sizeof(int), cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaMemcpyAsync(plan->tileFrom.p, req->tileFrom, T * sizeof(int), cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaMemcpyAsync(plan->tileTo.p, req->tileTo, T * sizeof(int), cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaMemcpyAsync(plan->order.p, order.data(), T * sizeof(int), cudaMemcpyHostToDevice, st));
+  }
+  if (seg) {
+    FSMC_CUDA(plan->scanFrom.ensure(T));
+    FSMC_CUDA(plan->scanTo.ensure(T));
+    FSMC_CUDA(plan->segments.ensure(plan->segmentCapacity));
+    if (T > 0) {
+      FSMC_CUDA(cudaMemcpyAsync(plan->scanFrom.p, req->tileScanFrom, T * sizeof(int), cudaMemcpyHostToDevice, st));
+      FSMC_CUDA(cudaMemcpyAsync(plan->scanTo.p, req->tileScanTo, T * sizeof(int), cudaMemcpyHostToDevice, st));
+    }
+  }
+  const size_t nSite = nLane * static_cast<size_t>(plan->siteStride);
+  if (flags & FSMC_SITE_MEAN) {
+    FSMC_CUDA(plan->siteMean.ensure(nSite));
+  }
+  if (flags & FSMC_SITE_MAP) {
+    FSMC_CUDA(plan->siteMap.ensure(nSite));
+  }
+  if (flags & FSMC_SITE_IBD) {
+    FSMC_CUDA(plan->siteIbd.ensure(nSite));
+  }
+  FSMC_CUDA(cudaStreamSynchronize(st));  // `order` is a local
+
+  // ---- launch geometry --------------------------------------------------------------------------
+  const KernelChoice kc = chooseKernel(m.S, flags);
+  plan->statesKernel = kc.statesKernel;
+  plan->mode = kc.mode;
+  int warpsPerBlock = kc.threads / 32;
+  const size_t perWarp = smemPerWarp(m, kc.mode, flags);
+  const size_t smemLimit = ctx->prop.sharedMemPerBlockOptin;
+  while (warpsPerBlock > 1 && perWarp * warpsPerBlock > smemLimit) {
+    warpsPerBlock /= 2;
+  }
+  if (perWarp * warpsPerBlock > smemLimit) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: %d states need %zu bytes of shared memory per warp (limit %zu)", m.S,
+                perWarp, smemLimit);
+  }
+  plan->threads = warpsPerBlock * 32;
+  plan->smemBytes = perWarp * warpsPerBlock;
+  FSMC_CUDA(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
+  int blocksPerSm = 0;
+  FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kc.fn, plan->threads, plan->smemBytes));
+  if (blocksPerSm < 1) {
+    return fail(FSMC_E_CUDA, "fsmc_plan_create: kernel does not fit on an SM (threads=%d smem=%zu)", plan->threads,
+                plan->smemBytes);
+  }
+  long long blocks = static_cast<long long>(ctx->prop.multiProcessorCount) * blocksPerSm;
+  blocks = std::min<long long>(blocks, (T + warpsPerBlock - 1) / warpsPerBlock);
+  blocks = std::max<long long>(blocks, 1);
+
+  // backward-sweep scratch: one slab of maxLen*S*32 floats per resident warp.  Shrink the grid if
+  // the slabs would not fit in 85% of the free memory.
+  plan->scratchPerWarp = maxLen * m.S * 32;
+  const size_t slabBytes = static_cast<size_t>(plan->scratchPerWarp) * sizeof(float);
+  if (slabBytes > 0) {
+    size_t freeB = 0, totalB = 0;
+    FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const size_t have = ctx->scratch.n * sizeof(float);
+    const size_t budget = static_cast<size_t>(0.85 * static_cast<double>(freeB + have));
+    long long maxWarps = static_cast<long long>(budget / slabBytes);
+    if (maxWarps < 1) {
+      return fail(FSMC_E_NOMEM, "fsmc_plan_create: a window of %lld sites needs a %zu-byte slab, %zu bytes free", maxLen,
+                  slabBytes, freeB);
+    }
+    blocks = std::min<long long>(blocks, std::max<long long>(1, maxWarps / warpsPerBlock));
+    if (blocks * warpsPerBlock > maxWarps) {
+      return fail(FSMC_E_NOMEM, "fsmc_plan_create: not enough device memory for one block's scratch");
+    }
+    FSMC_CUDA(ctx->scratch.ensure(static_cast<size_t>(blocks) * warpsPerBlock * plan->scratchPerWarp));
+  }
+  plan->blocks = static_cast<int>(blocks);
+  guard.keep = true;
+  *out = plan;
+  return FSMC_OK;
+}
+
+int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
+{
+  if (!ctx || !plan) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_launch: NULL argument");
+  }
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const DeviceModel& m = ctx->model;
+  FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
+  plan->launches = 0;
+  if (plan->numTiles > 0) {
+    FSMC_CUDA(cudaMemsetAsync(plan->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    DecodeArgs a{};
+    a.hapA = plan->hapA.p;
+    a.hapB = plan->hapB.p;
+    a.tilePairs = plan->tilePairs.p;
+    a.tileFrom = plan->tileFrom.p;
+    a.tileTo = plan->tileTo.p;
+    a.tileScanFrom = plan->scanFrom.p;
+    a.tileScanTo = plan->scanTo.p;
+    a.order = plan->order.p;
+    a.numTiles = plan->numTiles;
+    a.flags = plan->flags;
+    a.segments = plan->segments.p;
+    a.segmentCount = plan->counters.p;
+    a.segmentCapacity = plan->segmentCapacity;
+    a.siteMean = plan->siteMean.p;
+    a.siteMap = plan->siteMap.p;
+    a.siteIbd = plan->siteIbd.p;
+    a.siteStride = plan->siteStride;
+    a.scratch = ctx->scratch.p;
+    a.scratchPerWarp = plan->scratchPerWarp;
+    a.tileCounter = plan->counters.p + 1;
+    const KernelChoice kc = chooseKernel(m.S, plan->flags);
+    kc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(m, a);
+    FSMC_CUDA(cudaGetLastError());
+    plan->launches = 1;
+  }
+  FSMC_CUDA(cudaEventRecord(ctx->ev[2], st));
+  plan->launched = true;
+  return FSMC_OK;
+}
+
+int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request* out, fsmc_decode_stats* stats)
+{
+  if (!ctx || !plan || !out) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_collect: NULL argument");
+  }
+  if (!plan->launched) {
+    return fail(FSMC_E_STATE, "fsmc_plan_collect: plan was not launched");
+  }
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const unsigned flags = plan->flags;
+  unsigned long long counters[2] = {0, 0};
+  if (plan->numTiles > 0) {
+    FSMC_CUDA(cudaMemcpyAsync(counters, plan->counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+  }
+  FSMC_CUDA(cudaStreamSynchronize(st));
+  const long long found = static_cast<long long>(counters[0]);
+  const long long stored = std::min<long long>(found, plan->segmentCapacity);
+  int rc = FSMC_OK;
+  if (flags & FSMC_CALL_SEGMENTS) {
+    if (stored > 0) {
+      if (!out->segments || out->segmentCapacity < stored) {
+        return fail(FSMC_E_INVALID, "fsmc_plan_collect: segment buffer missing or smaller than at plan creation");
+      }
+      FSMC_CUDA(cudaMemcpyAsync(out->segments, plan->segments.p, stored * sizeof(fsmc_segment), cudaMemcpyDeviceToHost,
+                                st));
+    }
+  }
+  const size_t nSite = static_cast<size_t>(plan->numTiles) * 32 * static_cast<size_t>(plan->siteStride);
+  if ((flags & FSMC_SITE_MEAN) && nSite) {
+    if (!out->siteMean) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_collect: siteMean is NULL");
+    }
+    FSMC_CUDA(cudaMemcpyAsync(out->siteMean, plan->siteMean.p, nSite * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if ((flags & FSMC_SITE_MAP) && nSite) {
+    if (!out->siteMap) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_collect: siteMap is NULL");
+    }
+    FSMC_CUDA(cudaMemcpyAsync(out->siteMap, plan->siteMap.p, nSite * sizeof(int), cudaMemcpyDeviceToHost, st));
+  }
+  if ((flags & FSMC_SITE_IBD) && nSite) {
+    if (!out->siteIbd) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_collect: siteIbd is NULL");
+    }
+    FSMC_CUDA(cudaMemcpyAsync(out->siteIbd, plan->siteIbd.p, nSite * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  FSMC_CUDA(cudaEventRecord(ctx->ev[3], st));
+  FSMC_CUDA(cudaStreamSynchronize(st));
+  if (stored > 0) {
+    // reference order: batches in submission order, pairs in batch order, sites ascending
+    std::sort(out->segments, out->segments + stored, [](const fsmc_segment& x, const fsmc_segment& y) {
+      return x.pair != y.pair ? x.pair < y.pair : x.posStart < y.posStart;
+    });
+  }
+  if (found > plan->segmentCapacity) {
+    rc = fail(FSMC_E_OVERFLOW, "fsmc_plan_collect: %lld segments found, capacity %lld", found, plan->segmentCapacity);
+  }
+  if (stats) {
+    stats->numSegments = found;
+    stats->pairSites = plan->pairSites;
+    stats->kernelMs = 0.f;
+    stats->totalMs = 0.f;
+    cudaEventElapsedTime(&stats->kernelMs, ctx->ev[1], ctx->ev[2]);
+    if (cudaEventElapsedTime(&stats->totalMs, ctx->ev[0], ctx->ev[3]) != cudaSuccess) {
+      cudaGetLastError();
+      stats->totalMs = 0.f;
+    }
+    stats->kernelLaunches = plan->launches;
+    stats->statesKernel = plan->statesKernel;
+    stats->scratchBytes = static_cast<int64_t>(plan->scratchPerWarp) * sizeof(float) * plan->blocks * (plan->threads / 32);
+  }
+  plan->launched = false;
+  return rc;
+}
+
+int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan)
+{
+  if (ctx) {
+    cudaSetDevice(ctx->device);
+    cudaStreamSynchronize(ctx->stream);
+  }
+  delete plan;
+  return FSMC_OK;
+}
+
+int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats* stats)
+{
+  if (!ctx || !req) {
+    return fail(FSMC_E_INVALID, "fsmc_decode: NULL argument");
+  }
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  FSMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  fsmc_plan* plan = nullptr;
+  int rc = fsmc_plan_create(ctx, req, &plan);
+  if (rc != FSMC_OK) {
+    return rc;
+  }
+  rc = fsmc_plan_launch(ctx, plan);
+  if (rc == FSMC_OK) {
+    rc = fsmc_plan_collect(ctx, plan, req, stats);
+  }
+  const std::string keep = gLastError;
+  fsmc_plan_destroy(ctx, plan);
+  gLastError = keep;
+  return rc;
+}
+
+}  // extern "C"

@@ -1,0 +1,172 @@
+/*
+ * fastsmc_b200 — C ABI of the B200-native FastSMC IBD hot path (libfastsmc_b200.so).
+ *
+ * This is the drop-in boundary: plain pointers and sizes, int error codes, no exceptions, no C++
+ * or torch types.  The C++ host classes (fastsmc_b200/csrc/host: HMM, FastSMC, ASMC) and the
+ * Python front end call nothing else.  Each entry point names the reference routine(s) it
+ * replaces; paths are relative to the reference's ASMC_SRC/SRC directory.
+ *
+ * Conventions
+ *   - every function returns FSMC_OK (0) or a negative FSMC_E_* code; fsmc_last_error() returns a
+ *     thread-local message for the last failure on the calling thread;
+ *   - all pointers are HOST pointers unless a name ends in _dev;
+ *   - a context owns one GPU's device buffers and one CUDA stream; it is not re-entrant (like the
+ *     reference HMM object, HMM.hpp:84-170) — use one context per host thread and GPU;
+ *   - there is no CPU fallback: without a CUDA device every call fails with FSMC_E_CUDA.
+ */
+#ifndef FASTSMC_B200_H
+#define FASTSMC_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FSMC_OK 0
+#define FSMC_E_INVALID (-1)  /* bad argument                                        */
+#define FSMC_E_CUDA (-2)     /* CUDA runtime error (message has the CUDA string)    */
+#define FSMC_E_STATE (-3)    /* call order: model / haplotypes not set              */
+#define FSMC_E_OVERFLOW (-4) /* an output buffer was too small; see the out counts  */
+#define FSMC_E_NOMEM (-5)    /* device memory exhausted                             */
+
+#define FSMC_TILE 32 /* pairs per tile == lanes per warp == reference default batchSize */
+
+typedef struct fsmc_ctx fsmc_ctx;
+
+const char* fsmc_last_error(void);
+int fsmc_version(void);
+
+/* Number of visible CUDA devices (0 if none / driver missing). */
+int fsmc_device_count(void);
+
+/* Create / destroy a context on CUDA device `device`. */
+int fsmc_ctx_create(int device, fsmc_ctx** out);
+int fsmc_ctx_destroy(fsmc_ctx* ctx);
+
+/* Run all work of this context on an existing CUDA stream (a cudaStream_t passed as void*), e.g.
+ * torch's current stream.  NULL restores the context's own stream. */
+int fsmc_ctx_set_stream(fsmc_ctx* ctx, void* cuda_stream);
+
+/* ------------------------------------------------------------------------------------------------
+ * Model: everything HMM::HMM precomputes (HMM.cpp:65-127) and getNextAlphaBatched /
+ * getPreviousBetaBatched look up per site (HMM.cpp:795-797, 951-954).
+ *
+ * The reference keys transition rows by an exact float distance in an unordered_map
+ * (DecodingQuantities.hpp:60-63).  Here the host resolves roundMorgans(gen[pos]-gen[pos-1])
+ * (HmmUtils.cpp:65-79) to a row index once per site; the device sees dense tables.
+ * ------------------------------------------------------------------------------------------------ */
+typedef struct fsmc_model {
+  int32_t states;                 /* S                                                       */
+  int32_t sites;                  /* L                                                       */
+  const float* initialStateProb;  /* [S]    DecodingQuantities::initialStateProb             */
+  const float* expectedTimes;     /* [S]    DecodingQuantities::expectedTimes                */
+  const float* columnRatios;      /* [S]    DecodingQuantities::columnRatios                 */
+  const float* emission1;         /* [L][S] HMM::emission1AtSite        (HMM.cpp:159-256)    */
+  const float* emission0minus1;   /* [L][S] HMM::emission0minus1AtSite                       */
+  const float* emission2minus0;   /* [L][S] HMM::emission2minus0AtSite                       */
+  int32_t numDistances;           /* rows of the four transition tables                      */
+  const float* D;                 /* [numDistances][S] Dvectors                              */
+  const float* B;                 /* [numDistances][S] Bvectors                              */
+  const float* U;                 /* [numDistances][S] Uvectors                              */
+  const float* RR;                /* [numDistances][S] rowRatioVectors                       */
+  const int32_t* distanceRow;     /* [L] row for the gap (pos-1 -> pos); entry 0 is ignored  */
+  int32_t stateThreshold;         /* HMM::getStateThreshold   (HMM.cpp:504-513)              */
+  int32_t ageThreshold;           /* HMM.cpp:101-105                                         */
+  float probabilityThreshold;     /* HMM.cpp:96-99                                           */
+} fsmc_model;
+
+int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* model);
+
+/* ------------------------------------------------------------------------------------------------
+ * Haplotypes: the genotype1/genotype2 bit vectors of Data::individuals (Individual.hpp,
+ * Data.cpp:472-497), i.e. AFTER minor-allele folding, bit-packed.
+ * bits[h * wordsPerHap + s / 64] bit (s % 64) = allele of haplotype h at site s,
+ * wordsPerHap = (sites + 63) / 64.  Haplotype h is individual h/2, hap 1 + h%2
+ * (HmmUtils.cpp:179-188).
+ * ------------------------------------------------------------------------------------------------ */
+int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, int64_t numHaps, int64_t sites);
+
+/* ------------------------------------------------------------------------------------------------
+ * Decoding: replaces HMM::decodeBatch (HMM.cpp:639-722: forwardBatch, backwardBatch, combine) and
+ * its consumers writePerPairOutputFastSMC (HMM.cpp:1179-1357, segment calling incl.
+ * getPosteriorMean / getMAP, HMM.cpp:1087-1107) and writePerPairOutput (HMM.cpp:1360-1410).
+ *
+ * The unit of work is a TILE: up to 32 haplotype pairs that the reference decodes in one batch,
+ * sharing the batch's decode window [from,to) and segment-scan window [scanFrom,scanTo)
+ * (HMM.cpp:555-636, 1199-1204).  A reference batch larger than 32 is passed as several tiles with
+ * the same windows.  Per-site posteriors never leave the chip; only the outputs asked for do.
+ * ------------------------------------------------------------------------------------------------ */
+
+/* fsmc_decode_request.flags */
+#define FSMC_CALL_SEGMENTS 0x1u   /* run the IBD segment caller                                   */
+#define FSMC_SEG_AGE 0x2u         /* per-segment posterior mean + MAP (doPerPairPosteriorMean/MAP) */
+#define FSMC_SITE_MEAN 0x4u       /* per-site posterior mean TMRCA   (HMM.cpp:1378-1392)          */
+#define FSMC_SITE_MAP 0x8u        /* per-site MAP state index        (HMM.cpp:1396-1409)          */
+#define FSMC_SITE_IBD 0x10u       /* per-site IBD probability  sum_{k<stateThreshold} posterior   */
+#define FSMC_EXACT 0x20u          /* unfused mul/add in the reference's NO_SSE operation order:   */
+                                  /* results are bit-identical to the reference's NO_SSE build    */
+#define FSMC_GENERIC_KERNEL 0x40u /* force the any-S shared-memory kernel (testing)               */
+
+typedef struct fsmc_segment {
+  uint32_t pair;     /* tile * 32 + lane                                                        */
+  int32_t posStart;  /* first site of the segment                                               */
+  int32_t posEnd;    /* last site of the segment (inclusive)                                    */
+  float prob;        /* sum of per-site IBD probabilities (writePairIBD's `prob`)               */
+  float postMean;    /* HMM::getPosteriorMean of the per-state sums (if FSMC_SEG_AGE)           */
+  float mapTime;     /* HMM::getMAP: expectedTimes[argmax_k sum_k / prior_k] (if FSMC_SEG_AGE)  */
+  int32_t mapState;  /* that argmax                                                             */
+  int32_t level;     /* 0..3 = threshold 1000x,100x,10x,1x probabilityThreshold                 */
+} fsmc_segment;
+
+typedef struct fsmc_decode_request {
+  int64_t numTiles;
+  const uint32_t* hapA;        /* [numTiles*32] first haplotype of each pair  (unused lanes: any) */
+  const uint32_t* hapB;        /* [numTiles*32] second haplotype                                  */
+  const int32_t* tilePairs;    /* [numTiles] number of real pairs in the tile (1..32)             */
+  const int32_t* tileFrom;     /* [numTiles] decode window start                                  */
+  const int32_t* tileTo;       /* [numTiles] decode window end (exclusive)                        */
+  const int32_t* tileScanFrom; /* [numTiles] segment scan start   (ignored without CALL_SEGMENTS) */
+  const int32_t* tileScanTo;   /* [numTiles] segment scan end (exclusive)                         */
+  uint32_t flags;
+  /* outputs ------------------------------------------------------------------------------------ */
+  fsmc_segment* segments;      /* [segmentCapacity]; sorted by (pair, posStart) on return         */
+  int64_t segmentCapacity;
+  /* per-site outputs: row-major [numTiles*32][siteStride], row = pair, column = pos - tileFrom.
+   * Rows of unused lanes are left untouched.  May be NULL if the flag is not set. */
+  float* siteMean;
+  int32_t* siteMap;
+  float* siteIbd;
+  int64_t siteStride;
+} fsmc_decode_request;
+
+typedef struct fsmc_decode_stats {
+  int64_t numSegments;  /* segments found (may exceed segmentCapacity -> FSMC_E_OVERFLOW)         */
+  double pairSites;     /* sum over tiles of real pairs * (to - from)                             */
+  float kernelMs;       /* device time of the decode kernels, CUDA events on the context stream   */
+  float totalMs;        /* device time of the whole call incl. H2D/D2H copies on that stream      */
+  int32_t kernelLaunches;
+  int32_t statesKernel; /* S the kernel was specialised for, 0 = generic                          */
+  int64_t scratchBytes; /* backward-sweep scratch in HBM                                          */
+} fsmc_decode_stats;
+
+int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats* stats);
+
+/* Split-phase form of the same call, for callers that keep inputs resident in HBM and overlap host
+ * work with the kernels (and for timing the kernels without host traffic):
+ *   fsmc_plan_create  : validates the request, copies its input arrays to the device, allocates
+ *                       device outputs and the backward-sweep scratch;
+ *   fsmc_plan_launch  : enqueues the decode kernels on the context stream and returns at once;
+ *   fsmc_plan_collect : waits, copies the requested outputs into the host buffers of `out`
+ *                       (same layout as fsmc_decode_request; only the output fields are read) and
+ *                       sorts the segments.  May be called once per launch. */
+typedef struct fsmc_plan fsmc_plan;
+int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** out);
+int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan);
+int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request* out, fsmc_decode_stats* stats);
+int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FASTSMC_B200_H */

@@ -1,0 +1,154 @@
+"""GPU parity of the decode kernels (through the C ABI) against the CPU oracle on the reference's example data."""
+import numpy as np
+import pytest
+
+from conftest import FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, REGRESSION_PARAMS, context_from_oracle
+
+pytestmark = pytest.mark.gpu
+
+REL_TOL = 1e-4  # north-star tolerance on per-site posterior mean TMRCA and IBD probability
+
+
+@pytest.fixture(scope="module")
+def example(oracle_mod):
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test", hashing=True, **REGRESSION_PARAMS)
+    ctx = context_from_oracle(o, oracle_mod)
+    return o, ctx
+
+
+def _pairs(rng, n, num_haps):
+    a = rng.integers(0, num_haps, n)
+    b = rng.integers(0, num_haps, n)
+    b = np.where(a == b, (b + 1) % num_haps, b)
+    return a.astype(np.uint32), b.astype(np.uint32)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_per_site_outputs_exact_mode_bit_identical(example, generic):
+    """FSMC_EXACT reproduces the oracle's per-site posterior mean, MAP and IBD probability bit for bit."""
+    from fastsmc_b200 import _native as N
+    o, ctx = example
+    rng = np.random.default_rng(1)
+    a, b = _pairs(rng, 40, o.num_haps)
+    frm, to = 1000, 1700
+    mean, mp, ibd = o.decode_summary(a, b, frm, to)
+    tiles = ctx.make_tiles(a, b, windows=[[frm, to], [frm, to]], sites=o.sites)
+    flags = N.SITE_MEAN | N.SITE_MAP | N.SITE_IBD | N.EXACT | (N.GENERIC_KERNEL if generic else 0)
+    r = ctx.decode(tiles, flags)
+    rows = tiles["rows"]
+    assert r.stats.statesKernel == (0 if generic else 159)
+    assert np.array_equal(r.site_mean[rows, :to - frm].view(np.uint32), mean.view(np.uint32))
+    assert np.array_equal(r.site_ibd[rows, :to - frm].view(np.uint32), ibd.view(np.uint32))
+    assert np.array_equal(r.site_map[rows, :to - frm], mp)
+
+
+@pytest.mark.parametrize("generic", [False, True])
+def test_per_site_outputs_fast_mode_within_tolerance(example, generic):
+    from fastsmc_b200 import _native as N
+    o, ctx = example
+    rng = np.random.default_rng(2)
+    a, b = _pairs(rng, 64, o.num_haps)
+    frm, to = 0, 2500
+    mean, mp, ibd = o.decode_summary(a, b, frm, to)
+    tiles = ctx.make_tiles(a, b, windows=[[frm, to], [frm, to]], sites=o.sites)
+    r = ctx.decode(tiles, N.SITE_MEAN | N.SITE_MAP | N.SITE_IBD | (N.GENERIC_KERNEL if generic else 0))
+    rows = tiles["rows"]
+    np.testing.assert_allclose(r.site_mean[rows, :to - frm], mean, rtol=REL_TOL)
+    np.testing.assert_allclose(r.site_ibd[rows, :to - frm], ibd, rtol=REL_TOL, atol=1e-12)
+    # MAP may differ only where the two largest posteriors are within tolerance of each other
+    assert (r.site_map[rows, :to - frm] != mp).mean() < 1e-3
+
+
+def _oracle_segments(o):
+    ints, floats = o.segments()
+    return ints, floats
+
+
+@pytest.mark.parametrize("hashing", [True, False])
+def test_segments_exact_mode_identical_to_oracle(oracle_mod, hashing):
+    """Whole-job segment lists (golden G1 / G2 configurations): identical records in identical order."""
+    from fastsmc_b200 import _native as N
+    extra = dict(hashing=True) if hashing else dict(hashing=False, jobInd=7, jobs=9)
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test", **extra, **REGRESSION_PARAMS)
+    n = o.run("/tmp/fsmc_test_oracle.ibd.gz")
+    ints, floats = o.segments()
+    batches = o.batches()
+    ctx = context_from_oracle(o, oracle_mod)
+    # rebuild the pair stream from the oracle's segment-independent batch list
+    if hashing:
+        cands = o.candidates()
+        a, b = cands[:, 0], cands[:, 1]
+    else:
+        pytest.skip("covered by test_no_hashing_job_exact")
+    tiles = ctx.make_tiles(a, b, windows=batches[:, 3:5], scan=batches[:, 1:3], sites=o.sites)
+    r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE | N.EXACT)
+    seg = r.segments
+    assert len(seg) == n
+    assert np.array_equal(seg["pair"], ints[:, 0] * 32 + ints[:, 1])
+    assert np.array_equal(seg["posStart"], ints[:, 4])
+    assert np.array_equal(seg["posEnd"], ints[:, 5])
+    assert np.array_equal(seg["mapState"], ints[:, 6])
+    assert np.array_equal(seg["prob"].view(np.uint32), floats[:, 0].copy().view(np.uint32))
+    assert np.array_equal(seg["postMean"].view(np.uint32), floats[:, 1].copy().view(np.uint32))
+    assert np.array_equal(seg["mapTime"].view(np.uint32), floats[:, 2].copy().view(np.uint32))
+
+
+def test_segments_fast_mode_matches_oracle_within_tolerance(oracle_mod):
+    from fastsmc_b200 import _native as N
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test", hashing=True, **REGRESSION_PARAMS)
+    n = o.run("/tmp/fsmc_test_oracle.ibd.gz")
+    ints, floats = o.segments()
+    batches = o.batches()
+    cands = o.candidates()
+    ctx = context_from_oracle(o, oracle_mod)
+    tiles = ctx.make_tiles(cands[:, 0], cands[:, 1], windows=batches[:, 3:5], scan=batches[:, 1:3], sites=o.sites)
+    r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE)
+    seg = r.segments
+    # boundaries may move only at sites whose IBD probability is within tolerance of a threshold;
+    # on this data set none is, so the lists must coincide
+    assert len(seg) == n
+    assert np.array_equal(seg["pair"], ints[:, 0] * 32 + ints[:, 1])
+    assert np.array_equal(seg["posStart"], ints[:, 4])
+    assert np.array_equal(seg["posEnd"], ints[:, 5])
+    np.testing.assert_allclose(seg["prob"], floats[:, 0], rtol=REL_TOL)
+    np.testing.assert_allclose(seg["postMean"], floats[:, 1], rtol=REL_TOL)
+    assert (seg["mapState"] != ints[:, 6]).mean() < 5e-3
+
+
+def test_no_hashing_job_exact(oracle_mod):
+    """Golden G2 configuration (hashing off, job 7 of 9): all-pairs tiles over the whole sequence."""
+    from fastsmc_b200 import _native as N
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test", hashing=False, jobInd=7, jobs=9,
+                          **REGRESSION_PARAMS)
+    n = o.run("/tmp/fsmc_test_oracle_nohash.ibd.gz")
+    ints, floats = o.segments()
+    # pair stream: first record of each (batch, lane) is enough to recover hapA/hapB only for pairs with
+    # segments, so re-enumerate the job's pairs exactly as HMM::decodeAll does (HMM.cpp:311-357)
+    N_ind = o.num_haps // 2
+    tot = 2 * N_ind * N_ind - N_ind
+    lo, hi = tot * 6 // 9, tot * 7 // 9
+    a, b = [], []
+    idx = 0
+    for i in range(N_ind):
+        for j in range(i):
+            for ih in (0, 1):
+                for jh in (0, 1):
+                    if lo <= idx < hi:
+                        a.append(2 * j + jh)
+                        b.append(2 * i + ih)
+                    idx += 1
+        if lo <= idx < hi:
+            a.append(2 * i)
+            b.append(2 * i + 1)
+        idx += 1
+    ctx = context_from_oracle(o, oracle_mod)
+    tiles = ctx.make_tiles(np.array(a), np.array(b), sites=o.sites)
+    r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE | N.EXACT)
+    seg = r.segments
+    assert len(seg) == n == 2986
+    assert np.array_equal(seg["pair"], ints[:, 0] * 32 + ints[:, 1])
+    assert np.array_equal(seg["posStart"], ints[:, 4])
+    assert np.array_equal(seg["posEnd"], ints[:, 5])
+    assert np.array_equal(seg["prob"].view(np.uint32), floats[:, 0].copy().view(np.uint32))
+    assert np.array_equal(seg["postMean"].view(np.uint32), floats[:, 1].copy().view(np.uint32))
+    assert np.array_equal(seg["mapState"], ints[:, 6])
