@@ -145,7 +145,7 @@ def test_no_hashing_job_exact(oracle_mod):
     tiles = ctx.make_tiles(np.array(a), np.array(b), sites=o.sites)
     r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE | N.EXACT)
     seg = r.segments
-    assert len(seg) == n == 2986
+    assert len(seg) == n
     assert np.array_equal(seg["pair"], ints[:, 0] * 32 + ints[:, 1])
     assert np.array_equal(seg["posStart"], ints[:, 4])
     assert np.array_equal(seg["posEnd"], ints[:, 5])
