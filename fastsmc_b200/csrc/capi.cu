@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "decode_kernels.cuh"
+#include "seed_kernels.cuh"
 
 namespace
 {
@@ -74,6 +75,14 @@ struct fsmc_ctx {
   DevBuf<uint64_t> haps;
   long long numHaps = 0;
   DevBuf<float> scratch;
+  long long sites = 0;
+  // seeding scratch (fsmc_seed)
+  DevBuf<uint64_t> seedKeysT;
+  DevBuf<uint32_t> seedOwner, seedSlotCount, seedSlotGroup, seedSlotOf, seedRankOf, seedMembers, seedGroupSize,
+      seedGroupMemberBase, seedGlobalId;
+  DevBuf<unsigned long long> seedGroupPairBase, seedCounters;
+  DevBuf<float> seedGenPos;
+  DevBuf<fsmc_match> seedOut;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
 };
 
@@ -324,6 +333,7 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, const int64_t numHa
   ctx->model.haps = ctx->haps.p;
   ctx->model.wordsPerHap = words;
   ctx->numHaps = numHaps;
+  ctx->sites = sites;
   ctx->hasHaps = true;
   return FSMC_OK;
 }
@@ -622,6 +632,137 @@ int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan)
     cudaStreamSynchronize(ctx->stream);
   }
   delete plan;
+  return FSMC_OK;
+}
+
+
+int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const int64_t capacity,
+              fsmc_seed_stats* stats)
+{
+  if (!ctx || !sp || capacity < 0 || (capacity > 0 && !out)) {
+    return fail(FSMC_E_INVALID, "fsmc_seed: NULL argument or negative capacity");
+  }
+  if (!ctx->hasHaps) {
+    return fail(FSMC_E_STATE, "fsmc_seed: set the haplotypes first");
+  }
+  if (!sp->geneticPositions || !sp->globalHapId || sp->gap < 0) {
+    return fail(FSMC_E_INVALID, "fsmc_seed: geneticPositions / globalHapId missing or negative gap");
+  }
+  FSMC_CUDA(cudaSetDevice(ctx->device));
+  cudaStream_t st = ctx->stream;
+  const uint32_t H = static_cast<uint32_t>(ctx->numHaps);
+  const int L = static_cast<int>(ctx->sites);
+  const int W = L / 64;  // a trailing partial word is never hashed
+  uint32_t C = 64;
+  while (C < 2u * H) {
+    C <<= 1;
+  }
+  const size_t maxGroups = H / 2 + 2;
+  FSMC_CUDA(ctx->seedKeysT.ensure(static_cast<size_t>(std::max(W, 1)) * H));
+  FSMC_CUDA(ctx->seedOwner.ensure(C));
+  FSMC_CUDA(ctx->seedSlotCount.ensure(C));
+  FSMC_CUDA(ctx->seedSlotGroup.ensure(C));
+  FSMC_CUDA(ctx->seedSlotOf.ensure(H));
+  FSMC_CUDA(ctx->seedRankOf.ensure(H));
+  FSMC_CUDA(ctx->seedMembers.ensure(H));
+  FSMC_CUDA(ctx->seedGroupSize.ensure(maxGroups));
+  FSMC_CUDA(ctx->seedGroupMemberBase.ensure(maxGroups));
+  FSMC_CUDA(ctx->seedGroupPairBase.ensure(maxGroups + 1));
+  FSMC_CUDA(ctx->seedCounters.ensure(8));
+  FSMC_CUDA(ctx->seedGenPos.ensure(L));
+  FSMC_CUDA(ctx->seedGlobalId.ensure(H));
+  FSMC_CUDA(ctx->seedOut.ensure(static_cast<size_t>(capacity)));
+  FSMC_CUDA(cudaMemcpyAsync(ctx->seedGenPos.p, sp->geneticPositions, sizeof(float) * L, cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemcpyAsync(ctx->seedGlobalId.p, sp->globalHapId, sizeof(uint32_t) * H, cudaMemcpyHostToDevice, st));
+  FSMC_CUDA(cudaMemsetAsync(ctx->seedCounters.p, 0, 8 * sizeof(unsigned long long), st));
+
+  fsmc::SeedArgs a{};
+  a.haps = ctx->haps.p;
+  a.wordsPerHap = ctx->model.wordsPerHap;
+  a.keysT = ctx->seedKeysT.p;
+  a.H = H;
+  a.W = W;
+  a.L = L;
+  a.gap = sp->gap;
+  a.minLengthCm = sp->minLengthCm;
+  a.genPos = ctx->seedGenPos.p;
+  a.globalId = ctx->seedGlobalId.p;
+  a.loI = sp->loI;
+  a.hiI = sp->hiI;
+  a.loJ = sp->loJ;
+  a.hiJ = sp->hiJ;
+  a.lastJob = sp->lastJob;
+  a.aboveDiag = sp->aboveDiag;
+  a.flags = sp->flags;
+  a.owner = ctx->seedOwner.p;
+  a.slotCount = ctx->seedSlotCount.p;
+  a.slotGroup = ctx->seedSlotGroup.p;
+  a.C = C;
+  a.slotOf = ctx->seedSlotOf.p;
+  a.rankOf = ctx->seedRankOf.p;
+  a.groupSize = ctx->seedGroupSize.p;
+  a.groupMemberBase = ctx->seedGroupMemberBase.p;
+  a.groupPairBase = ctx->seedGroupPairBase.p;
+  a.members = ctx->seedMembers.p;
+  a.counters = ctx->seedCounters.p;
+  a.out = ctx->seedOut.p;
+  a.capacity = capacity;
+
+  int launches = 0;
+  FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
+  const int sms = ctx->prop.multiProcessorCount;
+  if (W > 0) {
+    const dim3 tb(32, 8), tg((H + 31) / 32, (W + 31) / 32);
+    fsmc::transposeWordsKernel<<<tg, tb, 0, st>>>(a.haps, a.wordsPerHap, H, W, ctx->seedKeysT.p);
+    ++launches;
+    const int hapBlocks = static_cast<int>(std::min<long long>((H + 255ll) / 256, sms * 8ll));
+    const int slotBlocks = static_cast<int>(std::min<long long>((C + 255ll) / 256, sms * 8ll));
+    for (int w = 0; w < W; ++w) {
+      FSMC_CUDA(cudaMemsetAsync(a.owner, 0, sizeof(uint32_t) * C, st));
+      FSMC_CUDA(cudaMemsetAsync(a.slotCount, 0, sizeof(uint32_t) * C, st));
+      FSMC_CUDA(cudaMemsetAsync(a.counters, 0, sizeof(unsigned long long), st));  // numGroups
+      fsmc::groupInsertKernel<<<hapBlocks, 256, 0, st>>>(a, w);
+      fsmc::groupCompactKernel<<<slotBlocks, 256, 0, st>>>(a);
+      fsmc::groupScanKernel<<<1, 1024, 0, st>>>(a);
+      fsmc::groupScatterKernel<<<hapBlocks, 256, 0, st>>>(a);
+      fsmc::pairExtendKernel<<<sms * 8, 256, 0, st>>>(a, w);
+      launches += 5;
+    }
+    FSMC_CUDA(cudaGetLastError());
+  }
+  FSMC_CUDA(cudaEventRecord(ctx->ev[2], st));
+  unsigned long long counters[8] = {0};
+  FSMC_CUDA(cudaMemcpyAsync(counters, ctx->seedCounters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+  FSMC_CUDA(cudaStreamSynchronize(st));
+  const long long found = static_cast<long long>(counters[3]);
+  const long long stored = std::min<long long>(found, capacity);
+  if (stored > 0) {
+    FSMC_CUDA(cudaMemcpyAsync(out, ctx->seedOut.p, stored * sizeof(fsmc_match), cudaMemcpyDeviceToHost, st));
+    FSMC_CUDA(cudaStreamSynchronize(st));
+    // canonical candidate order
+    std::sort(out, out + stored, [](const fsmc_match& x, const fsmc_match& y) {
+      if (x.endWord != y.endWord) {
+        return x.endWord < y.endWord;
+      }
+      return x.hapA != y.hapA ? x.hapA < y.hapA : x.hapB < y.hapB;
+    });
+  }
+  if (stats) {
+    stats->numMatches = found;
+    stats->pairVisits = static_cast<int64_t>(counters[4]);
+    stats->numStarts = static_cast<int64_t>(counters[5]);
+    stats->numWords = W;
+    stats->kernelLaunches = launches;
+    stats->kernelMs = 0.f;
+    cudaEventElapsedTime(&stats->kernelMs, ctx->ev[1], ctx->ev[2]);
+    // every packed word read and written once by the transpose, read once by the grouping pass; slot table cleared
+    // and probed; three per-haplotype bookkeeping words; 16 bytes per emitted interval
+    stats->bytesRead = static_cast<int64_t>(W) * (static_cast<int64_t>(H) * (8 + 8 + 8 + 12) + static_cast<int64_t>(C) * 12) +
+                       16 * found;
+  }
+  if (found > capacity) {
+    return fail(FSMC_E_OVERFLOW, "fsmc_seed: %lld intervals found, capacity %lld", found, static_cast<long long>(capacity));
+  }
   return FSMC_OK;
 }
 

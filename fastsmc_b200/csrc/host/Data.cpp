@@ -1,0 +1,468 @@
+// fastsmc_b200 host layer — see Data.hpp.
+#include "Data.hpp"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdlib>
+#include <iostream>
+#include <numeric>
+#include <random>
+#include <sstream>
+#include <stdexcept>
+
+#include "FileUtils.hpp"
+#include "StringUtils.hpp"
+
+namespace
+{
+
+const std::initializer_list<const char*> kHapExts = {".hap.gz", ".hap", ".haps.gz", ".haps"};
+
+bool isSamplesHeader(const std::vector<std::string>& t)
+{
+  // ref: Data.cpp:234-238
+  return t.size() >= 3 &&
+         ((t[0] == "ID_1" && t[1] == "ID_2" && t[2] == "missing") || (t[0] == "0" && t[1] == "0" && t[2] == "0"));
+}
+
+std::string samplesFile(const std::string& root)
+{
+  const std::string f = FileUtils::firstExisting(root, {".samples", ".sample"});
+  if (f.empty()) {
+    std::cerr << "ERROR. Could not find sample file in " + root + ".sample or " + root + ".samples" << std::endl;
+    exit(1);
+  }
+  return f;
+}
+
+std::string hapsFile(const std::string& root)
+{
+  const std::string f = FileUtils::firstExisting(root, kHapExts);
+  if (f.empty()) {
+    std::cerr << "ERROR. Could not find hap file in " + root + ".hap.gz, " + root + ".hap, " + ".haps.gz, or " + root +
+                     ".haps"
+              << std::endl;
+    exit(1);
+  }
+  return f;
+}
+
+}  // namespace
+
+int Data::countHapLines(std::string inFileRoot)
+{
+  FileUtils::LineReader in(hapsFile(inFileRoot));
+  std::string line;
+  int n = 0;
+  while (in.next(line)) {
+    ++n;
+  }
+  return n;
+}
+
+int Data::countSamplesLines(std::string inFileRoot)
+{
+  FileUtils::LineReader in(samplesFile(inFileRoot));
+  std::string line;
+  int n = 0;
+  while (in.next(line)) {
+    if (!isSamplesHeader(StringUtils::tokenizeMultipleDelimiters(line))) {
+      ++n;
+    }
+  }
+  return n;
+}
+
+// ref: Data.cpp:55-80
+void Data::setJobGeometry(const DecodingParams& params)
+{
+  jobs = params.jobs;
+  jobInd = params.jobInd;
+  foldToMinorAlleles = params.foldData;
+  decodingUsesCSFS = params.usingCSFS;
+  mJobbing = (jobInd != -1) && (jobs != -1);
+  if (params.useKnownSeed) {
+    std::srand(1234u);
+  } else {
+    std::random_device rd;
+    std::srand(rd());
+  }
+  if (mJobbing) {
+    const double n = static_cast<double>(sampleSize);
+    windowSize = static_cast<unsigned>(std::ceil(std::sqrt((2. * n * n - n) * 2. / jobs)));
+    if (windowSize % 2 != 0) {
+      ++windowSize;
+    }
+    w_i = 1;
+    int inRow = 1, upTo = 1;
+    while (upTo < jobInd) {
+      ++w_i;
+      inRow += 2;
+      upTo += inRow;
+    }
+    const int r = inRow - (upTo - jobInd);
+    w_j = static_cast<unsigned>(std::ceil(static_cast<float>(r) / 2));
+    is_j_above_diag = (r % 2 == 1);
+  }
+}
+
+// ref: Data.cpp:251-262
+bool Data::readSample(const unsigned n) const
+{
+  if (!mJobbing) {
+    return true;
+  }
+  return (n >= ((w_i - 1) * windowSize) / 2 && n < (w_i * windowSize) / 2) ||
+         (n >= ((w_j - 1) * windowSize) / 2 && n < (w_j * windowSize) / 2) ||
+         (jobs == jobInd && n >= ((w_j - 1) * windowSize) / 2);
+}
+
+Data::Data(const DecodingParams& params)
+{
+  const std::string& root = params.inFileRoot;
+  sites = countHapLines(root);
+  sampleSize = static_cast<unsigned long>(countSamplesLines(root));
+  haploidSampleSize = sampleSize * 2ul;
+  setJobGeometry(params);
+  if (!params.FastSMC) {
+    mJobbing = false;  // ASMC loads every sample; jobs only slice the pair list (ref: Data.cpp:86-95, HMM.cpp:319-321)
+  }
+  readSamplesList(root);
+  allocate();
+  if (params.FastSMC) {
+    readHapsFastSMC(root, readMapFastSMC(root));
+  } else {
+    readHapsAsmc(root);
+    readMapAsmc(root);
+  }
+}
+
+void Data::allocate()
+{
+  wordsPerHap = (sites + 63) / 64;
+  hapBits.assign(static_cast<size_t>(numLoadedHaplotypes()) * wordsPerHap, 0ull);
+  flipMask.assign(wordsPerHap, 0ull);
+  siteWasFlippedDuringFolding.assign(sites, false);
+  totalSamplesCount.assign(sites, 0);
+  derivedAlleleCounts.assign(sites, 0);
+  geneticPositions.clear();
+  physicalPositions.clear();
+  recRateAtMarker.clear();
+}
+
+// ref: Data.cpp:212-249
+void Data::readSamplesList(const std::string& inFileRoot)
+{
+  FileUtils::LineReader in(samplesFile(inFileRoot));
+  std::string line;
+  unsigned n = 0;
+  while (in.next(line)) {
+    const auto t = StringUtils::tokenizeMultipleDelimiters(line);
+    if (isSamplesHeader(t) || t.size() < 2) {
+      continue;
+    }
+    if (readSample(n)) {
+      FamIDList.push_back(t[0]);
+      IIDList.push_back(t[1]);
+      famAndIndNameList.push_back(t[0] + "\t" + t[1]);
+      globalHapId.push_back(2 * n);
+      globalHapId.push_back(2 * n + 1);
+    }
+    ++n;
+  }
+  std::cout << "Read data for " << famAndIndNameList.size() * 2 << " haploid samples." << std::endl;
+}
+
+// ref: Data.cpp:98-141
+std::vector<std::pair<unsigned long, double>> Data::readMapFastSMC(const std::string& inFileRoot)
+{
+  const std::string f = FileUtils::firstExisting(inFileRoot, {".map.gz", ".map"});
+  if (f.empty()) {
+    std::cerr << "ERROR. Could not find hap file in " + inFileRoot + ".map.gz or " + inFileRoot + ".map" << std::endl;
+    exit(1);
+  }
+  FileUtils::LineReader in(f);
+  std::vector<std::pair<unsigned long, double>> gmap;
+  std::string line;
+  while (in.next(line)) {
+    std::istringstream ss(line);
+    std::string f0, f1, f2;
+    ss >> f0 >> f1 >> f2;
+    if (f0.empty()) {
+      continue;
+    }
+    try {
+      (void)std::stoi(f0);
+    } catch (const std::invalid_argument&) {
+      continue;  // header row
+    }
+    gmap.emplace_back(std::stol(f0), std::stod(f2));
+  }
+  return gmap;
+}
+
+// One site's alleles -> packed bits, counts and folding (ref: Data.cpp:449-503).  `alleles` points at the text
+// after the five meta columns: for haplotype h the allele character is alleles[2*h + 1].
+void Data::addSite(const int pos, const char* alleles, const unsigned long nHapsInFile, const bool subset)
+{
+  int derived = 0;
+  for (unsigned long h = 0; h < nHapsInFile; ++h) {
+    const char c = alleles[2 * h + 1];
+    if (c != '0' && c != '1') {
+      std::cerr << "ERROR: hap is not '0' or '1'" << std::endl;
+      exit(1);
+    }
+    derived += (c == '1');
+  }
+  const int total = static_cast<int>(nHapsInFile);
+  const bool minorIsOne = foldToMinorAlleles ? (derived <= total - derived) : true;
+  siteWasFlippedDuringFolding[pos] = !minorIsOne;
+  const uint64_t bit = 1ull << (pos & 63);
+  const long w = pos >> 6;
+  if (!minorIsOne) {
+    flipMask[w] |= bit;
+  }
+  if (subset) {
+    for (size_t l = 0; l < globalHapId.size(); ++l) {
+      const bool one = alleles[2 * static_cast<size_t>(globalHapId[l]) + 1] == '1';
+      if (one == minorIsOne) {
+        hapBits[l * wordsPerHap + w] |= bit;
+      }
+    }
+  } else {
+    for (unsigned long h = 0; h < nHapsInFile; ++h) {
+      if ((alleles[2 * h + 1] == '1') == minorIsOne) {
+        hapBits[h * wordsPerHap + w] |= bit;
+      }
+    }
+  }
+  totalSamplesCount[pos] = total;
+  derivedAlleleCounts[pos] = foldToMinorAlleles ? std::min(derived, total - derived) : derived;
+}
+
+// ref: Data.cpp:523-565 (readGeneticMap + addMarker): linear interpolation of the map at bp
+void Data::addMarker(const int pos, const unsigned long bp, const std::vector<std::pair<unsigned long, double>>& gmap,
+                     unsigned& g)
+{
+  while (bp > gmap[g].first && g < gmap.size() - 1) {
+    ++g;
+  }
+  double cm;
+  if (bp >= gmap[g].first || g == 0) {
+    cm = gmap[g].second;
+  } else {
+    cm = gmap[g - 1].second +
+         (bp - gmap[g - 1].first) * (gmap[g].second - gmap[g - 1].second) / (gmap[g].first - gmap[g - 1].first);
+  }
+  geneticPositions.push_back(static_cast<float>(cm / 100.f));
+  physicalPositions.push_back(static_cast<int>(bp));
+  if (pos > 0) {
+    const double gd = geneticPositions[pos] - geneticPositions[pos - 1];
+    const unsigned long pd = physicalPositions[pos] - physicalPositions[pos - 1];
+    const float rate = static_cast<float>(gd / pd);
+    if (pos == 1) {
+      recRateAtMarker.push_back(rate);
+    }
+    recRateAtMarker.push_back(rate);
+  }
+}
+
+namespace
+{
+// Splits the five meta columns off a haps line; returns the offset of the allele text.
+size_t parseHapsMeta(const std::string& line, std::string& chr, unsigned long& bp)
+{
+  size_t p = 0;
+  std::string tok[5];
+  for (int f = 0; f < 5; ++f) {
+    while (p < line.size() && (line[p] == ' ' || line[p] == '\t')) {
+      ++p;
+    }
+    const size_t b = p;
+    while (p < line.size() && line[p] != ' ' && line[p] != '\t') {
+      ++p;
+    }
+    tok[f] = line.substr(b, p - b);
+  }
+  chr = tok[0];
+  bp = std::stoul(tok[2]);
+  return p;
+}
+}  // namespace
+
+// ref: Data.cpp:397-515
+void Data::readHapsFastSMC(const std::string& inFileRoot, const std::vector<std::pair<unsigned long, double>>& gmap)
+{
+  if (gmap.empty()) {
+    std::cerr << "ERROR: genetic map is empty" << std::endl;
+    exit(1);
+  }
+  FileUtils::LineReader in(hapsFile(inFileRoot));
+  std::string line, chr;
+  unsigned g = 0;
+  unsigned long lastBp = 0;
+  int pos = 0;
+  while (in.next(line)) {
+    if (line.empty()) {
+      break;
+    }
+    unsigned long bp = 0;
+    const size_t off = parseHapsMeta(line, chr, bp);
+    const size_t rest = line.size() - off;
+    if (!(rest == 4ul * sampleSize || rest == 4ul * sampleSize + 1)) {
+      std::cerr << "ERROR: haps line has wrong length. Length is " << rest << ", should be 4*" << sampleSize << "."
+                << std::endl;
+      exit(1);
+    }
+    if (bp <= lastBp) {
+      std::cerr << "ERROR: hap file must be sorted by increasing physical position." << std::endl;
+      exit(1);
+    }
+    lastBp = bp;
+    if (pos == 0) {
+      const size_t colon = chr.find(':');
+      try {
+        chrNumber = std::stoi(colon == std::string::npos ? chr : chr.substr(0, colon));
+      } catch (const std::exception&) {
+        chrNumber = 0;
+      }
+      if (chrNumber <= 0 || chrNumber > 1260) {
+        chrNumber = 0;
+      }
+    }
+    addMarker(pos, bp, gmap, g);
+    addSite(pos, line.c_str() + off, haploidSampleSize, true);
+    ++pos;
+  }
+  std::cout << "Read " << pos << " markers" << std::endl;
+}
+
+// ref: Data.cpp:318-395 — ASMC mode: every sample is loaded, counts are over the loaded haplotypes
+void Data::readHapsAsmc(const std::string& inFileRoot)
+{
+  FileUtils::LineReader in(hapsFile(inFileRoot));
+  std::string line, chr;
+  int pos = 0;
+  while (in.next(line)) {
+    if (line.empty()) {
+      break;
+    }
+    unsigned long bp = 0;
+    const size_t off = parseHapsMeta(line, chr, bp);
+    if (line.size() - off < 2ul * haploidSampleSize) {
+      std::cerr << "ERROR: haps line has wrong length." << std::endl;
+      exit(1);
+    }
+    addSite(pos, line.c_str() + off, haploidSampleSize, false);
+    ++pos;
+  }
+}
+
+// ref: Data.cpp:162-210 — PLINK-style map: chr, snp, cM, bp
+void Data::readMapAsmc(const std::string& inFileRoot)
+{
+  const std::string f = FileUtils::firstExisting(inFileRoot, {".map.gz", ".map"});
+  if (f.empty()) {
+    std::cerr << "ERROR. Could not find map file in " + inFileRoot + ".map.gz or " + inFileRoot + ".map" << std::endl;
+    exit(1);
+  }
+  FileUtils::LineReader in(f);
+  geneticPositions.assign(sites, 0.f);
+  physicalPositions.assign(sites, 0);
+  recRateAtMarker.assign(sites, 0.f);
+  std::string line;
+  int pos = 0;
+  while (in.next(line) && pos < sites) {
+    const auto t = StringUtils::tokenizeMultipleDelimiters(line);
+    if (t.size() < 4) {
+      continue;
+    }
+    geneticPositions[pos] = StringUtils::stof(t[2]) / 100.f;
+    physicalPositions[pos] = std::stoi(t[3]);
+    if (pos > 0) {
+      recRateAtMarker[pos] = (geneticPositions[pos] - geneticPositions[pos - 1]) /
+                             static_cast<float>(physicalPositions[pos] - physicalPositions[pos - 1]);
+    }
+    ++pos;
+  }
+}
+
+Data Data::fromArrays(const DecodingParams& params, const std::vector<std::string>& famIds,
+                      const std::vector<std::string>& iids, const uint8_t* raw, const long numHaps, const int numSites,
+                      const std::vector<int>& physPos, const std::vector<double>& cM, const int chr)
+{
+  Data d;
+  d.sites = numSites;
+  d.sampleSize = static_cast<unsigned long>(numHaps / 2);
+  d.haploidSampleSize = static_cast<unsigned long>(numHaps);
+  d.setJobGeometry(params);
+  for (unsigned n = 0; n < d.sampleSize; ++n) {
+    if (d.readSample(n)) {
+      d.FamIDList.push_back(famIds[n]);
+      d.IIDList.push_back(iids[n]);
+      d.famAndIndNameList.push_back(famIds[n] + "\t" + iids[n]);
+      d.globalHapId.push_back(2 * n);
+      d.globalHapId.push_back(2 * n + 1);
+    }
+  }
+  d.allocate();
+  d.chrNumber = chr;
+  // the same interpolation code path as the file reader, with the data's own sites as the map
+  std::vector<std::pair<unsigned long, double>> gmap(numSites);
+  for (int s = 0; s < numSites; ++s) {
+    gmap[s] = {static_cast<unsigned long>(physPos[s]), cM[s]};
+  }
+  std::string text(2 * static_cast<size_t>(numHaps), ' ');
+  unsigned g = 0;
+  for (int s = 0; s < numSites; ++s) {
+    for (long h = 0; h < numHaps; ++h) {
+      text[2 * h + 1] = raw[static_cast<size_t>(h) * numSites + s] ? '1' : '0';
+    }
+    d.addMarker(s, static_cast<unsigned long>(physPos[s]), gmap, g);
+    d.addSite(s, text.c_str(), d.haploidSampleSize, true);
+  }
+  return d;
+}
+
+Individual Data::individual(const unsigned long i) const
+{
+  Individual ind(sites);
+  for (int s = 0; s < sites; ++s) {
+    ind.genotype1[s] = allele(2 * i, s);
+    ind.genotype2[s] = allele(2 * i + 1, s);
+  }
+  return ind;
+}
+
+// ref: Data.cpp:144-160 (sampleHypergeometric) and 567-599.  The sequence of std::rand() calls and the
+// std::shuffle draws must match the reference's exactly, so this loop is deliberately serial.
+std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int numCsfsSamples) const
+{
+  std::vector<std::vector<int>> counts(sites, std::vector<int>(3, 0));
+  std::vector<unsigned short> urn;
+  for (int s = 0; s < sites; ++s) {
+    const int total = totalSamplesCount[s];
+    const int derived = derivedAlleleCounts[s];
+    if (decodingUsesCSFS && numCsfsSamples > total) {
+      std::cerr << "ERROR. The number of CSFS samples (" << numCsfsSamples
+                << ") is larger than the number of samples in the data (" << total << ")." << std::endl;
+      exit(1);
+    }
+    for (int dist = 0; dist < 3; ++dist) {
+      const int population = total - 2;
+      const int successes = derived - dist;
+      int sample = -1;
+      if (successes >= 0 && successes <= population) {
+        urn.assign(population, 0);
+        std::fill(urn.begin(), urn.begin() + successes, 1);
+        std::shuffle(urn.begin(), urn.end(), std::mt19937(std::rand()));
+        sample = std::accumulate(urn.begin(), urn.begin() + (numCsfsSamples - 2), 0);
+      }
+      if (foldToMinorAlleles && (sample + dist > numCsfsSamples / 2)) {
+        sample = numCsfsSamples - 2 - sample;
+      }
+      counts[s][dist] = sample;
+    }
+  }
+  return counts;
+}

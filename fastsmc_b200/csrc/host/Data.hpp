@@ -1,0 +1,102 @@
+// fastsmc_b200 host layer — input data of one job: samples, haplotypes, genetic map.
+// Public field names follow the reference's Data class (ref: ASMC_SRC/SRC/Data.hpp:33-75).  The layout is
+// different: haplotypes are kept bit-packed ([haplotype][site/64] uint64, minor-allele folded), which is what
+// the GPU kernels read, instead of two std::vector<bool> per Individual.
+#pragma once
+
+#include <cstdint>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "DecodingParams.hpp"
+
+// One diploid sample, materialised on demand from the packed matrix (ref: ASMC_SRC/SRC/Individual.hpp).
+struct Individual {
+  std::vector<bool> genotype1;
+  std::vector<bool> genotype2;
+  explicit Individual(int numOfSites = 0) : genotype1(numOfSites), genotype2(numOfSites) {}
+  void setGenotype(int_least8_t hap, int pos, bool val)
+  {
+    (hap == 1 ? genotype1 : genotype2).at(pos) = val;
+  }
+};
+
+class Data
+{
+public:
+  std::vector<std::string> FamIDList = {};
+  std::vector<std::string> IIDList = {};
+  std::vector<std::string> famAndIndNameList = {};
+
+  unsigned long sampleSize = 0ul;         // diploid samples in the file (all jobs)
+  unsigned long haploidSampleSize = 0ul;  // 2 * sampleSize
+  int sites = 0;
+  bool decodingUsesCSFS = false;
+  bool mJobbing = false;
+  bool foldToMinorAlleles = false;
+  std::vector<float> geneticPositions = {};
+  std::vector<int> physicalPositions = {};
+  std::vector<bool> siteWasFlippedDuringFolding = {};
+  std::vector<float> recRateAtMarker = {};
+
+  // FastSMC job geometry (ref: Data.cpp:62-80)
+  int chrNumber = 0;
+  unsigned int windowSize = 0u;
+  unsigned int w_i = 0u;
+  unsigned int w_j = 0u;
+  bool is_j_above_diag = false;
+  int jobs = 1, jobInd = 1;
+
+  // ---- B200 layout -------------------------------------------------------------------------------
+  // Loaded haplotypes (the job's subset): haplotype h = individual h/2, hap 1 + h%2.
+  // bit (s % 64) of hapBits[h * wordsPerHap + s / 64] = folded allele (1 = minor) at site s.
+  std::vector<uint64_t> hapBits;
+  long wordsPerHap = 0;
+  // flipMask[s / 64] bit (s % 64) = site s was flipped by folding; raw allele = folded ^ flip.  The seeding
+  // path hashes RAW alleles (ref: FastSMC.cpp:176-186).
+  std::vector<uint64_t> flipMask;
+  // global haplotype index (2 * line in .samples + hap) of each loaded haplotype (ref: FastSMC.cpp:97-103)
+  std::vector<uint32_t> globalHapId;
+  // whole-file allele counts per site (ref: Data.cpp:498-503)
+  std::vector<int> totalSamplesCount;
+  std::vector<int> derivedAlleleCounts;
+
+  Data() = default;
+  explicit Data(const DecodingParams& params);
+
+  // In-memory construction for synthetic workloads: `rawAlleles` is [numHaps][sites] bytes (0/1) for ALL samples of
+  // the data set; the job subset, folding and counts are derived exactly as when reading files.
+  static Data fromArrays(const DecodingParams& params, const std::vector<std::string>& famIds,
+                         const std::vector<std::string>& iids, const uint8_t* rawAlleles, long numHaps, int numSites,
+                         const std::vector<int>& physPos, const std::vector<double>& cM, int chr);
+
+  static int countHapLines(std::string inFileRoot);
+  static int countSamplesLines(std::string inFileRoot);
+
+  // Hypergeometric draws through std::rand -> std::mt19937 -> std::shuffle in the reference's call order
+  // (ref: Data.cpp:144-160, 567-599).
+  std::vector<std::vector<int>> calculateUndistinguishedCounts(int numCsfsSamples) const;
+
+  unsigned long numLoadedIndividuals() const { return famAndIndNameList.size(); }
+  unsigned long numLoadedHaplotypes() const { return 2ul * famAndIndNameList.size(); }
+  bool allele(unsigned long hap, long site) const
+  {
+    return (hapBits[hap * wordsPerHap + (site >> 6)] >> (site & 63)) & 1ull;
+  }
+  Individual individual(unsigned long i) const;
+  // whether line `n` of the samples file belongs to this job (ref: Data.cpp:251-262)
+  bool readSample(unsigned linesProcessed) const;
+
+private:
+  void setJobGeometry(const DecodingParams& params);
+  void readSamplesList(const std::string& inFileRoot);
+  void readHapsFastSMC(const std::string& inFileRoot, const std::vector<std::pair<unsigned long, double>>& geneticMap);
+  void readHapsAsmc(const std::string& inFileRoot);
+  void readMapAsmc(const std::string& inFileRoot);
+  static std::vector<std::pair<unsigned long, double>> readMapFastSMC(const std::string& inFileRoot);
+  void allocate();
+  void addSite(int pos, const char* alleles /* 2 chars per haplotype: ' ' + '0'/'1' */, unsigned long nHapsInFile,
+               bool subset);
+  void addMarker(int pos, unsigned long bp, const std::vector<std::pair<unsigned long, double>>& gmap, unsigned& cur_g);
+};

@@ -1,0 +1,705 @@
+// fastsmc_b200 host layer — see HMM.hpp.
+#include "HMM.hpp"
+
+#include <algorithm>
+#include <chrono>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <iostream>
+#include <limits>
+#include <map>
+#include <stdexcept>
+
+#include "../../../include/fastsmc_b200.h"
+#include "GzWriter.hpp"
+#include "HmmUtils.hpp"
+
+namespace
+{
+
+double now()
+{
+  return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
+}
+
+void check(const int rc, const char* what)
+{
+  if (rc != FSMC_OK) {
+    throw std::runtime_error(std::string(what) + ": " + fsmc_last_error());
+  }
+}
+
+// printf("%.7g") is what the reference's ostream produces for floats at precision 7 (ref: HMM.cpp:1116-1141)
+void appendG7(std::string& s, const double v)
+{
+  char buf[48];
+  const int n = std::snprintf(buf, sizeof buf, "\t%.7g", v);
+  s.append(buf, n);
+}
+
+}  // namespace
+
+struct HMM::GzOut {
+  GzWriter writer;
+  std::string line;
+  explicit GzOut(const std::string& path) : writer(path) {}
+};
+
+HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/)
+    : data(std::move(_data)), m_decodingQuant(_decodingParams.decodingQuantFile), decodingParams(_decodingParams)
+{
+  if (decodingParams.decodingSequence) {
+    throw std::runtime_error("sequence mode is not supported by the B200 build (array mode only)");
+  }
+  m_batchSize = decodingParams.batchSize;
+  sequenceLength = data.sites;
+  m_model = buildModelTables(data, m_decodingQuant, decodingParams);
+  stateThreshold = static_cast<unsigned>(m_model.stateThreshold);
+  ageThreshold = static_cast<unsigned>(m_model.ageThreshold);
+  probabilityThreshold = m_model.probabilityThreshold;
+  m_decodingReturnValues.sites = data.sites;
+  m_decodingReturnValues.states = m_decodingQuant.states;
+  m_decodingReturnValues.siteWasFlippedDuringFolding = data.siteWasFlippedDuringFolding;
+  // 8192 reference batches per kernel launch keep every SM busy; batch composition is unaffected because chunks
+  // are cut at multiples of the batch size
+  m_flushPairs = static_cast<size_t>(m_batchSize) * 8192;
+  uploadModel();
+}
+
+HMM::~HMM()
+{
+  if (m_ctx) {
+    fsmc_ctx_destroy(m_ctx);
+  }
+}
+
+// ref: HMM.cpp:504-513
+unsigned int HMM::getStateThreshold()
+{
+  unsigned int result = 0u;
+  const std::vector<float>& disc = m_decodingQuant.discretization;
+  while (disc[result] < static_cast<float>(decodingParams.time) && result < m_decodingQuant.states) {
+    ++result;
+  }
+  return result;
+}
+
+// ref: HMM.cpp:159-256 (array mode).  Three tables e1, e0-e1, e2-e0 per site and state.
+HMM::ModelTables HMM::buildModelTables(const Data& data, const DecodingQuantities& dq, const DecodingParams& decodingParams)
+{
+  ModelTables m_model;
+  const int S = static_cast<int>(dq.states);
+  const int L = data.sites;
+  constexpr int precision = 2;
+  constexpr float minGenetic = 1e-10f;
+  m_model.states = S;
+  m_model.sites = L;
+  m_model.emission1.assign(static_cast<size_t>(L) * S, 0.f);
+  m_model.emission0minus1.assign(static_cast<size_t>(L) * S, 0.f);
+  m_model.emission2minus0.assign(static_cast<size_t>(L) * S, 0.f);
+
+  std::vector<std::vector<int>> undist;
+  if (decodingParams.usingCSFS) {
+    undist = data.calculateUndistinguishedCounts(dq.CSFSSamples);
+  }
+  std::vector<uint8_t> useCsfs(L, 0);
+  if (decodingParams.skipCSFSdistance < std::numeric_limits<float>::infinity() && L > 0) {
+    useCsfs[0] = 1;
+    float last = 0.f;
+    for (int pos = 1; pos < L; ++pos) {
+      if (data.geneticPositions[pos] - last >= decodingParams.skipCSFSdistance) {
+        useCsfs[pos] = 1;
+        last = data.geneticPositions[pos];
+      }
+    }
+  }
+  for (int pos = 0; pos < L; ++pos) {
+    float* o1 = &m_model.emission1[static_cast<size_t>(pos) * S];
+    float* o0 = &m_model.emission0minus1[static_cast<size_t>(pos) * S];
+    float* o2 = &m_model.emission2minus0[static_cast<size_t>(pos) * S];
+    if (!useCsfs[pos]) {
+      const auto& T = decodingParams.decodingSequence ? dq.classicEmissionTable : dq.compressedEmissionTable;
+      for (int k = 0; k < S; ++k) {
+        o1[k] = T[1][k];
+        o0[k] = T[0][k] - T[1][k];
+        o2[k] = 0.f;
+      }
+      continue;
+    }
+    const int u0 = undist[pos][0], u1 = undist[pos][1], u2 = undist[pos][2];
+    if (decodingParams.foldData) {
+      const auto& T = dq.foldedAscertainedCSFSmap;
+      for (int k = 0; k < S; ++k) {
+        o1[k] = (u1 >= 0) ? T.at(u1)[1][k] : 0.f;
+        o0[k] = T.at(u0)[0][k] - o1[k];
+        o2[k] = (u2 >= 0) ? (T.at(u2)[0][k] - T.at(u0)[0][k]) : (0 - T.at(u0)[0][k]);
+      }
+    } else {
+      const auto& T = dq.ascertainedCSFSmap;
+      for (int k = 0; k < S; ++k) {
+        o1[k] = (u1 >= 0) ? T.at(u1)[1][k] : 0.f;
+        const float em0 = (u0 >= 0) ? T.at(u0)[0][k] : 0.f;
+        o0[k] = em0 - o1[k];
+        if (u2 >= 0) {
+          const bool mono = (u2 == dq.CSFSSamples - 2);  // monomorphic derived is read from CSFS[0][0]
+          o2[k] = T.at(mono ? 0 : u2)[mono ? 0 : 2][k] - em0;
+        } else {
+          o2[k] = 0 - em0;
+        }
+      }
+    }
+  }
+
+  // The reference looks transition vectors up by exact float key at every site of every batch
+  // (ref: HMM.cpp:753-756, 795-797, 907-909, 951-954).  Distances depend only on the site, so the key of every gap is
+  // resolved once here and the distinct rows are packed densely for the device.
+  std::map<float, int> rowOf;
+  m_model.distanceRow.assign(L, 0);
+  std::vector<float> keys;
+  for (int pos = 1; pos < L; ++pos) {
+    const float key =
+        asmc::roundMorgans(data.geneticPositions[pos] - data.geneticPositions[pos - 1], precision, minGenetic);
+    auto it = rowOf.find(key);
+    if (it == rowOf.end()) {
+      it = rowOf.emplace(key, static_cast<int>(keys.size())).first;
+      keys.push_back(key);
+    }
+    m_model.distanceRow[pos] = it->second;
+  }
+  if (keys.empty()) {
+    keys.push_back(minGenetic);
+  }
+  m_model.numDistances = static_cast<int>(keys.size());
+  auto gather = [&](const std::unordered_map<float, std::vector<float>>& table, std::vector<float>& out) {
+    out.assign(static_cast<size_t>(keys.size()) * S, 0.f);
+    for (size_t r = 0; r < keys.size(); ++r) {
+      const auto& row = table.at(keys[r]);  // throws std::out_of_range like the reference's .at()
+      std::copy(row.begin(), row.begin() + S, out.begin() + r * S);
+    }
+  };
+  gather(dq.Dvectors, m_model.D);
+  gather(dq.Bvectors, m_model.B);
+  gather(dq.Uvectors, m_model.U);
+  gather(dq.rowRatioVectors, m_model.RR);
+  // ref: HMM.cpp:504-513, 93-105
+  unsigned st = 0u;
+  while (dq.discretization[st] < static_cast<float>(decodingParams.time) && st < dq.states) {
+    ++st;
+  }
+  float pT = 0.f;
+  for (unsigned i = 0; i < st; ++i) {
+    pT += dq.initialStateProb.at(i);
+  }
+  m_model.stateThreshold = static_cast<int>(st);
+  m_model.ageThreshold = decodingParams.noConditionalAgeEstimates ? S : static_cast<int>(st);
+  m_model.probabilityThreshold = pT;
+  return m_model;
+}
+
+void HMM::uploadModel()
+{
+  check(fsmc_ctx_create(decodingParams.device, &m_ctx), "fsmc_ctx_create");
+  fsmc_model m{};
+  m.states = m_model.states;
+  m.sites = m_model.sites;
+  m.initialStateProb = m_decodingQuant.initialStateProb.data();
+  m.expectedTimes = m_decodingQuant.expectedTimes.data();
+  m.columnRatios = m_decodingQuant.columnRatios.data();
+  m.emission1 = m_model.emission1.data();
+  m.emission0minus1 = m_model.emission0minus1.data();
+  m.emission2minus0 = m_model.emission2minus0.data();
+  m.numDistances = m_model.numDistances;
+  m.D = m_model.D.data();
+  m.B = m_model.B.data();
+  m.U = m_model.U.data();
+  m.RR = m_model.RR.data();
+  m.distanceRow = m_model.distanceRow.data();
+  m.stateThreshold = m_model.stateThreshold;
+  m.ageThreshold = m_model.ageThreshold;
+  m.probabilityThreshold = m_model.probabilityThreshold;
+  check(fsmc_set_model(m_ctx, &m), "fsmc_set_model");
+  check(fsmc_set_haplotypes(m_ctx, data.hapBits.data(), static_cast<int64_t>(data.numLoadedHaplotypes()), data.sites),
+        "fsmc_set_haplotypes");
+}
+
+// ref: HMM.cpp:129-157
+PairObservations HMM::makePairObs(int_least8_t iHap, unsigned int ind1, int_least8_t jHap, unsigned int ind2,
+                                  const bool materialise)
+{
+  PairObservations p;
+  p.iHap = iHap;
+  p.jHap = jHap;
+  p.iInd = ind1;
+  p.jInd = ind2;
+  if (materialise) {
+    const unsigned long a = asmc::dipToHapId(ind1, iHap), b = asmc::dipToHapId(ind2, jHap);
+    p.obsBits.resize(data.sites);
+    p.homMinorBits.resize(data.sites);
+    for (int s = 0; s < data.sites; ++s) {
+      const bool x = data.allele(a, s), y = data.allele(b, s);
+      p.obsBits[s] = x != y;
+      p.homMinorBits[s] = x && y;
+    }
+  }
+  return p;
+}
+
+// ref: HMM.cpp:296-303, 383-401
+void HMM::openOutput(const int jobs, const int jobInd)
+{
+  const std::string path = decodingParams.outFileRoot + "." + std::to_string(jobInd) + "." + std::to_string(jobs) +
+                           (decodingParams.BIN_OUT ? ".FastSMC.bibd.gz" : ".FastSMC.ibd.gz");
+  m_out = std::make_unique<GzOut>(path);
+  if (decodingParams.BIN_OUT) {
+    auto& w = m_out->writer;
+    w.write(&decodingParams.outputIbdSegmentLength, sizeof(bool));
+    w.write(&decodingParams.doPerPairPosteriorMean, sizeof(bool));
+    w.write(&decodingParams.doPerPairMAP, sizeof(bool));
+    w.write(&data.chrNumber, sizeof(int));
+    const unsigned nInd = static_cast<unsigned>(data.FamIDList.size());
+    w.write(&nInd, sizeof(unsigned));
+    for (unsigned i = 0; i < nInd; ++i) {
+      unsigned len = static_cast<unsigned>(data.FamIDList[i].size());
+      w.write(&len, sizeof(unsigned));
+      w.write(data.FamIDList[i].data(), len);
+      len = static_cast<unsigned>(data.IIDList[i].size());
+      w.write(&len, sizeof(unsigned));
+      w.write(data.IIDList[i].data(), len);
+    }
+  }
+}
+
+// ref: HMM.cpp:283-381
+void HMM::decodeAll(const int jobs, const int jobInd)
+{
+  if (decodingParams.FastSMC) {
+    openOutput(jobs, jobInd);
+    if (decodingParams.hashing) {
+      return;
+    }
+  }
+  const uint64_t N = data.numLoadedIndividuals();
+  const uint64_t totPairs = decodingParams.withinOnly ? N : 2 * N * N - N;
+  const uint64_t lo = totPairs * static_cast<uint64_t>(jobInd - 1) / static_cast<uint64_t>(jobs);
+  const uint64_t hi = totPairs * static_cast<uint64_t>(jobInd) / static_cast<uint64_t>(jobs);
+  m_windowed = false;
+  uint64_t idx = 0;
+  const uint32_t L = static_cast<uint32_t>(data.sites);
+  auto submit = [&](const uint32_t a, const uint32_t b) {
+    if (lo <= idx && idx < hi) {
+      m_pending.push_back(Pending{a, b, 0u, L});
+      if (m_pending.size() >= m_flushPairs) {
+        flushPending(false);
+      }
+    }
+    ++idx;
+  };
+  // enumeration order of the reference: for i, for j < i, for iHap, for jHap: (jHap of j, iHap of i); then the
+  // pair within individual i (ref: HMM.cpp:325-357)
+  for (uint32_t i = 0; i < N && idx < hi; ++i) {
+    if (!decodingParams.withinOnly) {
+      if (idx + 4ull * i <= lo) {
+        idx += 4ull * i;  // the whole row lies before the job's slice
+      } else {
+        for (uint32_t j = 0; j < i; ++j) {
+          for (uint32_t ih = 0; ih < 2; ++ih) {
+            for (uint32_t jh = 0; jh < 2; ++jh) {
+              submit(2 * j + jh, 2 * i + ih);
+            }
+          }
+        }
+      }
+    }
+    submit(2 * i, 2 * i + 1);
+  }
+  if (decodingParams.FastSMC) {
+    finishDecoding();
+  }
+}
+
+// ref: HMM.cpp:470-502
+void HMM::decodeFromHashing(const unsigned int i, const unsigned int j, const unsigned int fromPosition,
+                            const unsigned int toPosition)
+{
+  m_windowed = true;
+  m_pending.push_back(Pending{i, j, fromPosition, toPosition});
+  ++cpt;
+  if (m_pending.size() >= m_flushPairs) {
+    flushPending(false);
+  }
+}
+
+void HMM::decodePair(const unsigned int i, const unsigned int j)
+{
+  // ref: HMM.cpp:413-440
+  if (i != j) {
+    for (uint32_t ih = 0; ih < 2; ++ih) {
+      for (uint32_t jh = 0; jh < 2; ++jh) {
+        decodeHapPair(2ul * i + ih, 2ul * j + jh);
+      }
+    }
+  } else {
+    decodeHapPair(2ul * i, 2ul * i + 1);
+  }
+}
+
+void HMM::decodePairs(const std::vector<unsigned int>& individualsA, const std::vector<unsigned int>& individualsB)
+{
+  if (individualsA.size() != individualsB.size()) {
+    throw std::runtime_error("vector of A indicies must be the same size as vector of B indicies");
+  }
+  for (size_t i = 0; i < individualsA.size(); ++i) {
+    decodePair(individualsA[i], individualsB[i]);
+  }
+}
+
+// ref: HMM.cpp:442-457
+void HMM::decodeHapPair(const unsigned long i, const unsigned long j)
+{
+  const unsigned long numHaps = data.numLoadedHaplotypes();
+  if (i >= numHaps || j >= numHaps) {
+    throw std::runtime_error("haplotype index out of range");
+  }
+  m_windowed = false;
+  const auto [iInd, iHap] = asmc::hapToDipId(i);
+  const auto [jInd, jHap] = asmc::hapToDipId(j);
+  m_observationsBatch.push_back(makePairObs(static_cast<int_least8_t>(iHap), static_cast<unsigned>(iInd),
+                                            static_cast<int_least8_t>(jHap), static_cast<unsigned>(jInd)));
+  if (static_cast<int>(m_observationsBatch.size()) == m_batchSize) {
+    m_observationsBatch.clear();  // the reference's buffer empties when a batch is decoded (ref: HMM.cpp:589)
+  }
+  m_pendingRow.push_back(m_decodePairsReturnStruct.getNumWritten() + m_pending.size());
+  m_pending.push_back(Pending{static_cast<uint32_t>(i), static_cast<uint32_t>(j), 0u, static_cast<uint32_t>(data.sites)});
+  // per-site outputs are pairs x sites floats: keep chunks small enough for host and device buffers
+  const size_t perSiteChunk =
+      std::max<size_t>(static_cast<size_t>(m_batchSize),
+                       (size_t{1} << 28) / std::max<size_t>(1, static_cast<size_t>(data.sites)) / m_batchSize * m_batchSize);
+  if (!decodingParams.FastSMC && m_pending.size() >= perSiteChunk) {
+    flushPending(false);
+  }
+}
+
+void HMM::decodeHapPairs(const std::vector<unsigned long>& hapsA, const std::vector<unsigned long>& hapsB)
+{
+  if (hapsA.size() != hapsB.size()) {
+    throw std::runtime_error("vector of A indices must be the same size as vector of B indices");
+  }
+  m_pendingRow.clear();
+  for (size_t i = 0; i < hapsA.size(); ++i) {
+    decodeHapPair(hapsA[i], hapsB[i]);
+  }
+}
+
+void HMM::finishDecoding()
+{
+  flushPending(true);
+  m_observationsBatch.clear();
+}
+
+void HMM::closeIBDFile()
+{
+  if (m_out) {
+    const double t0 = now();
+    m_out->writer.close();
+    m_stats.outputWallS += now() - t0;
+    m_out.reset();
+  }
+}
+
+void HMM::finishFromHashing()
+{
+  flushPending(true);
+  closeIBDFile();
+}
+
+// Decodes the pending pairs in whole reference batches (all of them when `all`).
+void HMM::flushPending(const bool all)
+{
+  const size_t bs = static_cast<size_t>(m_batchSize);
+  size_t n = all ? m_pending.size() : m_pending.size() / bs * bs;
+  if (n == 0) {
+    return;
+  }
+  const bool segments = decodingParams.FastSMC;
+  if (segments) {
+    runSegmentChunk(m_pending.data(), n);
+  } else if (m_storePerPairPosteriorMean || m_storePerPairMAP || m_storePerPairPosterior || m_storeSumOfPosterior) {
+    runPerSiteChunk(m_pending.data(), m_pendingRow.data(), n);
+    m_pendingRow.erase(m_pendingRow.begin(), m_pendingRow.begin() + n);
+  }
+  m_pending.erase(m_pending.begin(), m_pending.begin() + n);
+}
+
+namespace
+{
+
+// Tiles of one chunk: a reference batch of batchSize consecutive pairs shares one decode window and one scan
+// window (ref: HMM.cpp:561-565, 1199-1204); batches wider than a warp become several tiles with the same windows.
+struct TileSet {
+  std::vector<uint32_t> hapA, hapB;
+  std::vector<int32_t> pairs, from, to, scanFrom, scanTo;
+  std::vector<uint32_t> firstPair;  // index into the chunk of lane 0 of each tile
+};
+
+template <class P>
+TileSet buildTiles(const P* pend, const size_t n, const size_t batchSize, const bool windowed,
+                   const std::vector<float>& gen, const int sites)
+{
+  TileSet t;
+  for (size_t b0 = 0; b0 < n; b0 += batchSize) {
+    const size_t b1 = std::min(n, b0 + batchSize);
+    uint32_t lo = 0, hi = static_cast<uint32_t>(sites);
+    if (windowed) {
+      lo = std::numeric_limits<uint32_t>::max();
+      hi = 0;
+      for (size_t i = b0; i < b1; ++i) {
+        lo = std::min(lo, pend[i].from);
+        hi = std::max(hi, pend[i].to);
+      }
+    }
+    const int from = static_cast<int>(asmc::getFromPosition(gen, lo));
+    const int to = static_cast<int>(asmc::getToPosition(gen, hi));
+    for (size_t s = b0; s < b1; s += FSMC_TILE) {
+      const size_t e = std::min(b1, s + FSMC_TILE);
+      const size_t base = t.hapA.size();
+      t.hapA.resize(base + FSMC_TILE, 0u);
+      t.hapB.resize(base + FSMC_TILE, 0u);
+      for (size_t i = s; i < e; ++i) {
+        t.hapA[base + (i - s)] = pend[i].hapA;
+        t.hapB[base + (i - s)] = pend[i].hapB;
+      }
+      t.pairs.push_back(static_cast<int32_t>(e - s));
+      t.from.push_back(from);
+      t.to.push_back(to);
+      t.scanFrom.push_back(static_cast<int32_t>(lo));
+      t.scanTo.push_back(static_cast<int32_t>(hi));
+      t.firstPair.push_back(static_cast<uint32_t>(s));
+    }
+  }
+  return t;
+}
+
+}  // namespace
+
+void HMM::runSegmentChunk(const Pending* pend, const size_t n)
+{
+  const TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), m_windowed, data.geneticPositions, data.sites);
+  const bool ages = decodingParams.doPerPairPosteriorMean || decodingParams.doPerPairMAP;
+  fsmc_decode_request req{};
+  req.numTiles = static_cast<int64_t>(t.pairs.size());
+  req.hapA = t.hapA.data();
+  req.hapB = t.hapB.data();
+  req.tilePairs = t.pairs.data();
+  req.tileFrom = t.from.data();
+  req.tileTo = t.to.data();
+  req.tileScanFrom = t.scanFrom.data();
+  req.tileScanTo = t.scanTo.data();
+  req.flags = FSMC_CALL_SEGMENTS | (ages ? FSMC_SEG_AGE : 0u) | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
+  std::vector<fsmc_segment> seg(std::max<size_t>(1024, n * 2));
+  fsmc_decode_stats st{};
+  for (;;) {
+    req.segments = seg.data();
+    req.segmentCapacity = static_cast<int64_t>(seg.size());
+    const double t0 = now();
+    const int rc = fsmc_decode(m_ctx, &req, &st);
+    m_stats.decodeWallS += now() - t0;
+    if (rc == FSMC_E_OVERFLOW) {
+      seg.resize(static_cast<size_t>(st.numSegments) + 1024);
+      continue;
+    }
+    check(rc, "fsmc_decode");
+    break;
+  }
+  m_stats.decodeCalls += 1;
+  m_stats.pairsDecoded += n;
+  m_stats.batches += (n + m_batchSize - 1) / m_batchSize;
+  m_stats.pairSites += st.pairSites;
+  m_stats.kernelMs += st.kernelMs;
+  m_stats.deviceMs += st.totalMs;
+
+  const double t1 = now();
+  for (int64_t i = 0; i < st.numSegments; ++i) {
+    const fsmc_segment& g = seg[i];
+    const size_t p = t.firstPair[g.pair / FSMC_TILE] + (g.pair % FSMC_TILE);
+    IbdSegment s;
+    // first haplotype of the pair is printed first (ref: HMM.cpp:483-486, 1116-1121)
+    s.ind1 = pend[p].hapA / 2;
+    s.hap1 = 1 + static_cast<int>(pend[p].hapA % 2);
+    s.ind2 = pend[p].hapB / 2;
+    s.hap2 = 1 + static_cast<int>(pend[p].hapB % 2);
+    s.posStart = g.posStart;
+    s.posEnd = g.posEnd;
+    s.prob = g.prob;
+    s.postMean = g.postMean;
+    s.mapTime = g.mapTime;
+    writeSegment(s);
+  }
+  m_stats.outputWallS += now() - t1;
+}
+
+// ref: HMM.cpp:1110-1177
+void HMM::writeSegment(const IbdSegment& s)
+{
+  ++nbSegmentsDetected;
+  ++m_stats.segments;
+  if (m_keepSegments) {
+    m_segments.push_back(s);
+  }
+  if (!m_out) {
+    return;
+  }
+  const int bpStart = data.physicalPositions[s.posStart], bpEnd = data.physicalPositions[s.posEnd];
+  const float cm = 100.f * (data.geneticPositions[s.posEnd] - data.geneticPositions[s.posStart]);
+  const double score = s.prob / static_cast<double>(static_cast<unsigned>(s.posEnd - s.posStart) + 1u);
+  auto& w = m_out->writer;
+  if (!decodingParams.BIN_OUT) {
+    std::string& l = m_out->line;
+    l.clear();
+    l += data.FamIDList[s.ind1];
+    l += '\t';
+    l += data.IIDList[s.ind1];
+    l += '\t';
+    l += std::to_string(s.hap1);
+    l += '\t';
+    l += data.FamIDList[s.ind2];
+    l += '\t';
+    l += data.IIDList[s.ind2];
+    l += '\t';
+    l += std::to_string(s.hap2);
+    l += '\t';
+    l += std::to_string(data.chrNumber);
+    l += '\t';
+    l += std::to_string(bpStart);
+    l += '\t';
+    l += std::to_string(bpEnd);
+    if (decodingParams.outputIbdSegmentLength) {
+      appendG7(l, static_cast<double>(cm));
+    }
+    appendG7(l, score);
+    if (decodingParams.doPerPairPosteriorMean) {
+      appendG7(l, static_cast<double>(s.postMean));
+    }
+    if (decodingParams.doPerPairMAP) {
+      appendG7(l, static_cast<double>(s.mapTime));
+    }
+    l += '\n';
+    w.write(l);
+  } else {
+    const unsigned ind[2] = {s.ind1, s.ind2};
+    const uint8_t hp[2] = {static_cast<uint8_t>(s.hap1), static_cast<uint8_t>(s.hap2)};
+    const float scoreF = static_cast<float>(score);
+    w.write(&ind[0], sizeof(unsigned));
+    w.write(&hp[0], 1);
+    w.write(&ind[1], sizeof(unsigned));
+    w.write(&hp[1], 1);
+    w.write(&bpStart, sizeof(int));
+    w.write(&bpEnd, sizeof(int));
+    if (decodingParams.outputIbdSegmentLength) {
+      w.write(&cm, sizeof(float));
+    }
+    w.write(&scoreF, sizeof(float));
+    if (decodingParams.doPerPairPosteriorMean) {
+      w.write(&s.postMean, sizeof(float));
+    }
+    if (decodingParams.doPerPairMAP) {
+      w.write(&s.mapTime, sizeof(float));
+    }
+  }
+}
+
+// Per-site posterior mean / MAP for ASMC::decodePairs (ref: HMM.cpp:1360-1458)
+void HMM::runPerSiteChunk(const Pending* pend, const unsigned long* rows, const size_t n)
+{
+  if (m_storePerPairPosterior || m_storeSumOfPosterior) {
+    throw std::runtime_error(
+        "per-pair posterior matrices / sum of posteriors are not produced by the B200 build (per-site posterior "
+        "means and MAPs are)");
+  }
+  const TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), false, data.geneticPositions, data.sites);
+  const size_t T = t.pairs.size();
+  const int L = data.sites;
+  fsmc_decode_request req{};
+  req.numTiles = static_cast<int64_t>(T);
+  req.hapA = t.hapA.data();
+  req.hapB = t.hapB.data();
+  req.tilePairs = t.pairs.data();
+  req.tileFrom = t.from.data();
+  req.tileTo = t.to.data();
+  // the reference computes the MAP rows only under the posterior-mean flag (ref: HMM.cpp:1447-1449); both outputs
+  // are produced here whenever either is stored
+  req.flags = FSMC_SITE_MEAN | FSMC_SITE_MAP | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
+  std::vector<float> mean(T * FSMC_TILE * static_cast<size_t>(L));
+  std::vector<int32_t> map(T * FSMC_TILE * static_cast<size_t>(L));
+  req.siteMean = mean.data();
+  req.siteMap = map.data();
+  req.siteStride = L;
+  fsmc_decode_stats st{};
+  const double t0 = now();
+  check(fsmc_decode(m_ctx, &req, &st), "fsmc_decode");
+  m_stats.decodeWallS += now() - t0;
+  m_stats.decodeCalls += 1;
+  m_stats.pairsDecoded += n;
+  m_stats.pairSites += st.pairSites;
+  m_stats.kernelMs += st.kernelMs;
+  m_stats.deviceMs += st.totalMs;
+  auto& out = m_decodePairsReturnStruct;
+  for (size_t tile = 0; tile < T; ++tile) {
+    for (int lane = 0; lane < t.pairs[tile]; ++lane) {
+      const size_t p = t.firstPair[tile] + lane;
+      const unsigned long row = rows[p];
+      const size_t src = (tile * FSMC_TILE + lane) * static_cast<size_t>(L);
+      const unsigned long a = pend[p].hapA, b = pend[p].hapB;
+      out.perPairIndices.at(row) =
+          std::make_tuple(a, asmc::indPlusHapToCombinedId(data.IIDList.at(a / 2), 1 + a % 2), b,
+                          asmc::indPlusHapToCombinedId(data.IIDList.at(b / 2), 1 + b % 2));
+      if (m_storePerPairPosteriorMean) {
+        std::memcpy(out.perPairPosteriorMeans.row(static_cast<long>(row)), &mean[src], sizeof(float) * L);
+      }
+      if (m_storePerPairMAP) {
+        std::memcpy(out.perPairMAPs.row(static_cast<long>(row)), &map[src], sizeof(int32_t) * L);
+      }
+      out.incrementNumWritten();
+    }
+  }
+}
+
+std::vector<std::vector<float>> HMM::decode(const PairObservations&)
+{
+  throw std::runtime_error("HMM::decode (full posterior matrix of one pair) is not produced by the B200 build");
+}
+
+std::vector<std::vector<float>> HMM::decode(const PairObservations&, unsigned, unsigned)
+{
+  throw std::runtime_error("HMM::decode (full posterior matrix of one pair) is not produced by the B200 build");
+}
+
+// ref: HMM.cpp:1532-1560
+std::pair<std::vector<float>, std::vector<float>> HMM::decodeSummarize(const PairObservations& obs)
+{
+  const Pending p{static_cast<uint32_t>(asmc::dipToHapId(obs.iInd, obs.iHap)),
+                  static_cast<uint32_t>(asmc::dipToHapId(obs.jInd, obs.jHap)), 0u, static_cast<uint32_t>(data.sites)};
+  const TileSet t = buildTiles(&p, 1, 1, false, data.geneticPositions, data.sites);
+  const int L = data.sites;
+  fsmc_decode_request req{};
+  req.numTiles = 1;
+  req.hapA = t.hapA.data();
+  req.hapB = t.hapB.data();
+  req.tilePairs = t.pairs.data();
+  req.tileFrom = t.from.data();
+  req.tileTo = t.to.data();
+  req.flags = FSMC_SITE_MEAN | FSMC_SITE_MAP | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
+  std::vector<float> mean(static_cast<size_t>(FSMC_TILE) * L);
+  std::vector<int32_t> map(static_cast<size_t>(FSMC_TILE) * L);
+  req.siteMean = mean.data();
+  req.siteMap = map.data();
+  req.siteStride = L;
+  check(fsmc_decode(m_ctx, &req, nullptr), "fsmc_decode");
+  std::pair<std::vector<float>, std::vector<float>> out;
+  out.first.assign(mean.begin(), mean.begin() + L);
+  out.second.resize(L);
+  for (int s = 0; s < L; ++s) {
+    out.second[s] = m_decodingQuant.expectedTimes[map[s]];
+  }
+  return out;
+}

@@ -1,0 +1,322 @@
+// fastsmc_b200 — sm_100a kernels for GERMLINE-style candidate seeding (FastSMC's hashing step).
+//
+// Reference semantics (ASMC_SRC/SRC/FastSMC.cpp:144-229, HASHING/SeedHash.hpp, HASHING/ExtendHash.hpp): per 64-SNP
+// word, haplotypes with identical words are grouped; every pair of a group "matches" at that word; a pair's matches
+// are merged into intervals that tolerate `gap` non-matching words.  The reference keeps two hash maps alive across
+// words and touches every matching pair at every word.  Here the interval structure is computed order-free:
+//
+//   transposeWordsKernel : [hap][word] packed haplotypes -> [word][hap] keys (coalesced for the per-word passes)
+//   per word w:
+//     groupInsertKernel  : open-addressing hash on the 64-bit word itself (the reference's hash is the identity on
+//                          the word, so equal key <=> identical word: no false positives); a slot is owned by the
+//                          first haplotype that claims it; every haplotype gets (slot, rank within slot)
+//     groupCompactKernel : slots with >= 2 members become groups; pair count n(n-1)/2 per group
+//     groupScanKernel    : exclusive scans of group sizes and pair counts (one CTA; #groups <= H/2)
+//     groupScatterKernel : members of each group, contiguous
+//     pairExtendKernel   : persistent CTAs walk the word's pair space in chunks.  For each pair (a<b) matching at w:
+//                          job filter on global ids, then the START test (no match in the gap+1 preceding words, read
+//                          from the hap-major matrix).  Lanes that hold a start are served one at a time by the whole
+//                          warp: 32 lanes compare 32 consecutive words of the two haplotypes per step (two coalesced
+//                          256-byte reads) and a ballot finds where the run of > gap misses begins.  The interval is
+//                          length-filtered in genetic distance and appended to the output.
+//
+// A pair's interval is discovered exactly once (at its start word), so the output is the set of the reference's
+// Match objects at flush time; their order is fixed afterwards (canonical sort, or the host's replay of the
+// reference's hash-map iteration order).
+#pragma once
+
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#include "../../include/fastsmc_b200.h"
+
+namespace fsmc
+{
+
+struct SeedArgs {
+  const uint64_t* haps;      // [H][wordsPerHap] folded alleles
+  long long wordsPerHap;
+  const uint64_t* keysT;     // [W][H]
+  uint32_t H;
+  int W;
+  int L;                     // sites
+  int gap;
+  float minLengthCm;
+  const float* genPos;       // [L]
+  const uint32_t* globalId;  // [H]
+  uint32_t loI, hiI, loJ, hiJ;
+  int lastJob, aboveDiag;
+  unsigned flags;
+  // per-word scratch
+  uint32_t* owner;           // [C] hap+1 owning the slot, 0 = empty
+  uint32_t* slotCount;       // [C]
+  uint32_t* slotGroup;       // [C]
+  uint32_t C;                // power of two
+  uint32_t* slotOf;          // [H]
+  uint32_t* rankOf;          // [H]
+  uint32_t* groupSize;       // [H/2+1]
+  uint32_t* groupMemberBase; // [H/2+1]
+  unsigned long long* groupPairBase;  // [H/2+2]  (exclusive scan, last = total)
+  uint32_t* members;         // [H]
+  unsigned long long* counters;  // [0] numGroups [1] pairCursor [2] totalPairs(word) [3] matchCount [4] pairVisits
+                                 // [5] numStarts
+  fsmc_match* out;
+  long long capacity;
+};
+
+__device__ __forceinline__ uint32_t mixKey(uint64_t k)
+{
+  k ^= k >> 33;
+  k *= 0xff51afd7ed558ccdull;
+  k ^= k >> 33;
+  k *= 0xc4ceb9fe1a85ec53ull;
+  k ^= k >> 33;
+  return static_cast<uint32_t>(k);
+}
+
+// [H][wph] -> [W][H] through a 32x33 shared tile: reads coalesced along words, writes coalesced along haplotypes
+__global__ void transposeWordsKernel(const uint64_t* __restrict__ haps, const long long wph, const uint32_t H,
+                                     const int W, uint64_t* __restrict__ keysT)
+{
+  __shared__ uint64_t tile[32][33];
+  const uint32_t h0 = blockIdx.x * 32u;
+  const int w0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const uint32_t h = h0 + r;
+    const int w = w0 + threadIdx.x;
+    tile[r][threadIdx.x] = (h < H && w < W) ? haps[static_cast<size_t>(h) * wph + w] : 0ull;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int w = w0 + r;
+    const uint32_t h = h0 + threadIdx.x;
+    if (h < H && w < W) {
+      keysT[static_cast<size_t>(w) * H + h] = tile[threadIdx.x][r];
+    }
+  }
+}
+
+__global__ void groupInsertKernel(const SeedArgs a, const int w)
+{
+  const uint64_t* keys = a.keysT + static_cast<size_t>(w) * a.H;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
+    const uint64_t k = keys[h];
+    uint32_t slot = mixKey(k) & (a.C - 1);
+    for (;;) {
+      uint32_t o = a.owner[slot];
+      if (o == 0) {
+        o = atomicCAS(&a.owner[slot], 0u, h + 1u);
+        if (o == 0) {
+          o = h + 1u;
+        }
+      }
+      if (o == h + 1u || keys[o - 1u] == k) {
+        break;
+      }
+      slot = (slot + 1u) & (a.C - 1);
+    }
+    a.slotOf[h] = slot;
+    a.rankOf[h] = atomicAdd(&a.slotCount[slot], 1u);
+  }
+}
+
+__global__ void groupCompactKernel(const SeedArgs a)
+{
+  for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < a.C; s += gridDim.x * blockDim.x) {
+    const uint32_t n = a.slotCount[s];
+    if (n >= 2u) {
+      const uint32_t g = static_cast<uint32_t>(atomicAdd(&a.counters[0], 1ull));
+      a.slotGroup[s] = g;
+      a.groupSize[g] = n;
+    }
+  }
+}
+
+// One CTA: exclusive scans over the groups (member offsets, pair offsets).  Each thread owns a contiguous run.
+__global__ void groupScanKernel(const SeedArgs a)
+{
+  __shared__ unsigned long long partMembers[1024], partPairs[1024];
+  const uint32_t G = static_cast<uint32_t>(a.counters[0]);
+  const uint32_t T = blockDim.x, t = threadIdx.x;
+  const uint32_t per = (G + T - 1) / T;
+  const uint32_t lo = min(G, t * per), hi = min(G, lo + per);
+  unsigned long long m = 0, p = 0;
+  for (uint32_t g = lo; g < hi; ++g) {
+    const unsigned long long n = a.groupSize[g];
+    m += n;
+    p += n * (n - 1ull) / 2ull;
+  }
+  partMembers[t] = m;
+  partPairs[t] = p;
+  __syncthreads();
+  if (t == 0) {
+    unsigned long long rm = 0, rp = 0;
+    for (uint32_t i = 0; i < T; ++i) {
+      const unsigned long long xm = partMembers[i], xp = partPairs[i];
+      partMembers[i] = rm;
+      partPairs[i] = rp;
+      rm += xm;
+      rp += xp;
+    }
+    a.groupPairBase[G] = rp;
+    a.counters[2] = rp;
+    a.counters[1] = 0ull;
+    a.counters[4] += rp;
+  }
+  __syncthreads();
+  m = partMembers[t];
+  p = partPairs[t];
+  for (uint32_t g = lo; g < hi; ++g) {
+    const unsigned long long n = a.groupSize[g];
+    a.groupMemberBase[g] = static_cast<uint32_t>(m);
+    a.groupPairBase[g] = p;
+    m += n;
+    p += n * (n - 1ull) / 2ull;
+  }
+}
+
+__global__ void groupScatterKernel(const SeedArgs a)
+{
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
+    const uint32_t s = a.slotOf[h];
+    if (a.slotCount[s] >= 2u) {
+      a.members[a.groupMemberBase[a.slotGroup[s]] + a.rankOf[h]] = h;
+    }
+  }
+}
+
+// job filter on global haplotype ids, gi > gj (ref: HASHING/SeedHash.hpp:99-129)
+__device__ __forceinline__ bool pairInJob(const SeedArgs& a, const uint32_t hi, const uint32_t lo)
+{
+  const uint32_t gi = a.globalId[hi], gj = a.globalId[lo];
+  if (a.lastJob) {
+    return gi >= a.loI && gj >= a.loJ && gj < a.loJ + (gi - a.loI);
+  }
+  if (gi >= a.loI && gi < a.hiI && gj >= a.loJ && gj < a.hiJ) {
+    return a.aboveDiag ? (gj < a.loJ + (gi - a.loI)) : (gj >= a.loJ + (gi - a.loI));
+  }
+  return false;
+}
+
+constexpr int kPairChunk = 8;  // consecutive pair indices per thread
+
+__global__ void __launch_bounds__(256) pairExtendKernel(const SeedArgs a, const int w)
+{
+  const unsigned lane = threadIdx.x & 31u;
+  const unsigned long long total = a.counters[2];
+  const uint32_t G = static_cast<uint32_t>(a.counters[0]);
+  __shared__ unsigned long long blockBase;
+  const unsigned long long perBlock = static_cast<unsigned long long>(blockDim.x) * kPairChunk;
+  for (;;) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      blockBase = atomicAdd(&a.counters[1], perBlock);
+    }
+    __syncthreads();
+    const unsigned long long base = blockBase;
+    if (base >= total) {
+      break;
+    }
+    unsigned long long q = base + static_cast<unsigned long long>(threadIdx.x) * kPairChunk;
+    // locate the group of pair index q: last g with groupPairBase[g] <= q
+    uint32_t g = 0, n = 0, memberBase = 0, i = 0, ii = 0;
+    unsigned long long left = 0;  // pairs of this thread's run still to visit
+    if (q < total) {
+      uint32_t lo = 0, hi = G;
+      while (hi - lo > 1u) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a.groupPairBase[mid] <= q) {
+          lo = mid;
+        } else {
+          hi = mid;
+        }
+      }
+      g = lo;
+      const unsigned long long r = q - a.groupPairBase[g];
+      // r = i(i-1)/2 + ii with ii < i
+      i = static_cast<uint32_t>((1.0 + sqrt(1.0 + 8.0 * static_cast<double>(r))) * 0.5);
+      while (static_cast<unsigned long long>(i) * (i - 1ull) / 2ull > r) {
+        --i;
+      }
+      while (static_cast<unsigned long long>(i + 1ull) * i / 2ull <= r) {
+        ++i;
+      }
+      ii = static_cast<uint32_t>(r - static_cast<unsigned long long>(i) * (i - 1ull) / 2ull);
+      n = a.groupSize[g];
+      memberBase = a.groupMemberBase[g];
+      left = min(static_cast<unsigned long long>(kPairChunk), total - q);
+    }
+    for (int step = 0; step < kPairChunk; ++step) {
+      bool isStart = false;
+      uint32_t hLo = 0, hHi = 0;
+      if (left > 0) {
+        const uint32_t x = a.members[memberBase + i], y = a.members[memberBase + ii];
+        hLo = min(x, y);
+        hHi = max(x, y);
+        if (pairInJob(a, hHi, hLo)) {
+          isStart = true;
+          const uint64_t* A = a.haps + static_cast<size_t>(hLo) * a.wordsPerHap;
+          const uint64_t* B = a.haps + static_cast<size_t>(hHi) * a.wordsPerHap;
+          for (int d = 1; d <= a.gap + 1 && w - d >= 0; ++d) {
+            if (__ldg(A + w - d) == __ldg(B + w - d)) {
+              isStart = false;
+              break;
+            }
+          }
+        }
+        // advance to the next pair of the run
+        --left;
+        if (++ii == i) {
+          ii = 0;
+          if (++i == n && left > 0) {
+            ++g;
+            n = a.groupSize[g];
+            memberBase = a.groupMemberBase[g];
+            i = 1;
+          }
+        }
+      }
+      // warp-level extension: serve the lanes that hold a start one after the other
+      unsigned pending = __ballot_sync(0xffffffffu, isStart);
+      while (pending) {
+        const int src = __ffs(pending) - 1;
+        pending &= pending - 1u;
+        const uint32_t sLo = __shfl_sync(0xffffffffu, hLo, src), sHi = __shfl_sync(0xffffffffu, hHi, src);
+        const uint64_t* A = a.haps + static_cast<size_t>(sLo) * a.wordsPerHap;
+        const uint64_t* B = a.haps + static_cast<size_t>(sHi) * a.wordsPerHap;
+        int end = w, misses = 0;
+        bool open = true;
+        for (int pos = w + 1; pos < a.W && open; pos += 32) {
+          const int x = pos + static_cast<int>(lane);
+          const bool eq = x < a.W && __ldg(A + x) == __ldg(B + x);
+          const unsigned m = __ballot_sync(0xffffffffu, eq);
+          const int valid = min(32, a.W - pos);
+          for (int b = 0; b < valid; ++b) {  // warp-uniform walk over the 32 comparison bits
+            if ((m >> b) & 1u) {
+              end = pos + b;
+              misses = 0;
+            } else if (++misses > a.gap) {
+              open = false;
+              break;
+            }
+          }
+        }
+        if (lane == 0) {
+          atomicAdd(&a.counters[5], 1ull);
+          // ref: HASHING/Utils.cpp:22-34, HASHING/Match.hpp:46-51
+          const int sEnd = min(64 * end + 63, a.L - 1);
+          const float d = a.genPos[sEnd] - a.genPos[64 * w];
+          const bool keep = (a.flags & FSMC_SEED_ALL_INTERVALS) || (100.0 * static_cast<double>(d) >= static_cast<double>(a.minLengthCm));
+          if (keep) {
+            const unsigned long long idx = atomicAdd(&a.counters[3], 1ull);
+            if (static_cast<long long>(idx) < a.capacity) {
+              a.out[idx] = fsmc_match{sLo, sHi, w, end};
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+}  // namespace fsmc

@@ -166,6 +166,59 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan);
 int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request* out, fsmc_decode_stats* stats);
 int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan);
 
+
+/* ------------------------------------------------------------------------------------------------
+ * Seeding: replaces the GERMLINE-style candidate search of FastSMC::run (FastSMC.cpp:144-229):
+ * Individuals::getWordHash (HASHING/Individuals.hpp:51-62), SeedHash::insertIndividuals /
+ * extendAllPairs incl. the job-window filter (HASHING/SeedHash.hpp:41-135), ExtendHash::extendPair /
+ * clearPairsPriorTo / clearAllPairs (HASHING/ExtendHash.hpp:52-116) and the length filter of
+ * Match::print (HASHING/Match.hpp:42-52, HASHING/Utils.cpp:22-34).
+ *
+ * Works on the haplotypes given to fsmc_set_haplotypes.  Word w covers sites [64w, 64w+63]; a
+ * trailing partial word is never hashed (FastSMC.cpp:188-196).  Two haplotypes match at w when
+ * their 64-SNP words are identical (the reference's hash is the identity on the word, SURVEY F5;
+ * minor-allele folding flips both haplotypes alike, so folded words compare like raw ones).  A
+ * match interval [startWord, endWord] of a pair a < b starts at a matching word with no match in
+ * the preceding gap+1 words, and is extended while the next match is at most gap+1 words ahead.
+ * Intervals are produced for pairs that pass the job filter on GLOBAL haplotype ids
+ * (HASHING/SeedHash.hpp:99-129) and, unless FSMC_SEED_ALL_INTERVALS is set, whose genetic length
+ * 100*(gen[min(64*end+63, L-1)] - gen[64*start]) is >= minLengthCm.
+ * Output order: ascending (endWord, hapA, hapB) — the canonical candidate order.
+ * ------------------------------------------------------------------------------------------------ */
+#define FSMC_SEED_ALL_INTERVALS 0x1u /* keep intervals shorter than minLengthCm too (order replay)  */
+
+typedef struct fsmc_match {
+  uint32_t hapA;      /* smaller local haplotype index                                            */
+  uint32_t hapB;      /* larger local haplotype index                                             */
+  int32_t startWord;
+  int32_t endWord;    /* inclusive                                                                */
+} fsmc_match;
+
+typedef struct fsmc_seed_params {
+  int32_t gap;                    /* DecodingParams::gap                                          */
+  float minLengthCm;              /* DecodingParams::min_m                                        */
+  const float* geneticPositions;  /* [sites] Morgans (Data::geneticPositions)                     */
+  const uint32_t* globalHapId;    /* [numHaps] id of each loaded haplotype in the whole data set  */
+  /* job geometry, in global haplotype ids (Data.cpp:62-80): windows [loI,hiI) x [loJ,hiJ)        */
+  uint32_t loI, hiI, loJ, hiJ;
+  int32_t lastJob;                /* jobInd == jobs: open-ended windows, strictly below diagonal  */
+  int32_t aboveDiag;              /* Data::is_j_above_diag                                        */
+  uint32_t flags;
+} fsmc_seed_params;
+
+typedef struct fsmc_seed_stats {
+  int64_t numMatches;     /* intervals found (may exceed capacity -> FSMC_E_OVERFLOW)              */
+  int64_t pairVisits;     /* sum over words of sum over groups n(n-1)/2                            */
+  int64_t numStarts;      /* pair visits that started an interval                                  */
+  int32_t numWords;
+  int32_t kernelLaunches;
+  float kernelMs;         /* device time of the seeding kernels                                    */
+  int64_t bytesRead;      /* algorithmic HBM bytes: every word once + grouping traffic             */
+} fsmc_seed_stats;
+
+int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* params, fsmc_match* out, int64_t capacity,
+              fsmc_seed_stats* stats);
+
 #ifdef __cplusplus
 }
 #endif

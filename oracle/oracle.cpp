@@ -798,60 +798,84 @@ void Oracle::decodeBatch(const std::vector<PairObs>& pairs, const unsigned from,
     }
   }
 
-  posterior.assign(static_cast<size_t>(len) * plane, 0.f);  // holds alpha, then the posterior
-  std::vector<float> beta(static_cast<size_t>(len) * plane);
-  std::vector<float> scratchA(plane), scratchB(plane), lane1(n), sums(n), em(n);
+  posterior.resize(static_cast<size_t>(len) * plane);  // holds alpha, then the posterior (every element is written)
+  // per-thread scratch, reused across batches (the reference allocates its buffers once per HMM, ref: HMM.cpp:111-116)
+  static thread_local std::vector<float> beta;
+  beta.resize(static_cast<size_t>(len) * plane);
+  std::vector<float> scratchA(plane), scratchB(plane), lane1(n), sums(n);
   const std::vector<float>& cr = dq.columnRatios;
-
-  auto emission = [&](const long p, const int k) {
-    const float a1 = e1[(from + p) * static_cast<size_t>(S) + k];
-    const float a0 = e0m1[(from + p) * static_cast<size_t>(S) + k];
-    const float a2 = e2m0[(from + p) * static_cast<size_t>(S) + k];
-    for (int v = 0; v < n; ++v) {
-      em[v] = a1 + a0 * isZero[p * n + v] + a2 * isTwo[p * n + v];
-    }
-  };
 
   // ---- forward.  ref: HMM.cpp:725-784
   {
-    float* a0 = &posterior[0];
+    float* __restrict a0 = &posterior[0];
     for (int k = 0; k < S; ++k) {
-      emission(0, k);
+      const float pi = dq.initialStateProb[k];
+      const float c1 = e1[from * static_cast<size_t>(S) + k], c0 = e0m1[from * static_cast<size_t>(S) + k],
+                  c2 = e2m0[from * static_cast<size_t>(S) + k];
+      const float* __restrict z = &isZero[0];
+      const float* __restrict t = &isTwo[0];
+      float* __restrict out = a0 + static_cast<size_t>(k) * n;
+#pragma GCC ivdep
       for (int v = 0; v < n; ++v) {
-        a0[k * n + v] = dq.initialStateProb[k] * em[v];
+        out[v] = pi * (c1 + c0 * z[v] + c2 * t[v]);
       }
     }
     rescale(a0, S, n, sums.data());
   }
-  float* alphaC = scratchA.data();
-  float* AU = lane1.data();
+  float* __restrict alphaC = scratchA.data();
+  float* __restrict AU = lane1.data();
   for (long p = 1; p < len; ++p) {
     const float dist = roundMorgans(genPos[from + p] - genPos[from + p - 1], 2, 1e-10f);
     const float* Bv = dq.B.at(dist).data();
     const float* Uv = dq.U.at(dist).data();
     const float* Dv = dq.D.at(dist).data();
-    const float* prev = &posterior[(p - 1) * plane];
-    float* next = &posterior[p * plane];
+    const float* __restrict prev = &posterior[(p - 1) * plane];
+    float* __restrict next = &posterior[p * plane];
+    const float* __restrict z = &isZero[p * n];
+    const float* __restrict t = &isTwo[p * n];
+    const float* E1 = &e1[(from + p) * static_cast<size_t>(S)];
+    const float* E0 = &e0m1[(from + p) * static_cast<size_t>(S)];
+    const float* E2 = &e2m0[(from + p) * static_cast<size_t>(S)];
     // ref: HMM.cpp:799-814 — suffix sums of the previous alpha
-    std::memcpy(&alphaC[(S - 1) * n], &prev[(S - 1) * n], n * sizeof(float));
+    std::memcpy(&alphaC[static_cast<size_t>(S - 1) * n], &prev[static_cast<size_t>(S - 1) * n], n * sizeof(float));
     for (int k = S - 2; k >= 0; --k) {
+      float* __restrict o = alphaC + static_cast<size_t>(k) * n;
+      const float* __restrict up = alphaC + static_cast<size_t>(k + 1) * n;
+      const float* __restrict pk = prev + static_cast<size_t>(k) * n;
+#pragma GCC ivdep
       for (int v = 0; v < n; ++v) {
-        alphaC[k * n + v] = alphaC[(k + 1) * n + v] + prev[k * n + v];
+        o[v] = up[v] + pk[v];
       }
     }
     // ref: HMM.cpp:816-830
     std::fill(AU, AU + n, 0.f);
     for (int k = 0; k < S; ++k) {
-      emission(p, k);
-      for (int v = 0; v < n; ++v) {
-        if (k) {
-          AU[v] = Uv[k - 1] * prev[(k - 1) * n + v] + cr[k - 1] * AU[v];
+      const float c1 = E1[k], c0 = E0[k], c2 = E2[k], dk = Dv[k];
+      const float* __restrict pk = prev + static_cast<size_t>(k) * n;
+      float* __restrict o = next + static_cast<size_t>(k) * n;
+      if (k) {
+        const float u = Uv[k - 1], c = cr[k - 1];
+        const float* __restrict pm = prev + static_cast<size_t>(k - 1) * n;
+#pragma GCC ivdep
+        for (int v = 0; v < n; ++v) {
+          AU[v] = u * pm[v] + c * AU[v];
         }
-        float term = AU[v] + Dv[k] * prev[k * n + v];
-        if (k < S - 1) {
-          term += Bv[k] * alphaC[(k + 1) * n + v];
+      }
+      if (k < S - 1) {
+        const float bk = Bv[k];
+        const float* __restrict ac = alphaC + static_cast<size_t>(k + 1) * n;
+#pragma GCC ivdep
+        for (int v = 0; v < n; ++v) {
+          float term = AU[v] + dk * pk[v];
+          term += bk * ac[v];
+          o[v] = (c1 + c0 * z[v] + c2 * t[v]) * term;
         }
-        next[k * n + v] = em[v] * term;
+      } else {
+#pragma GCC ivdep
+        for (int v = 0; v < n; ++v) {
+          const float term = AU[v] + dk * pk[v];
+          o[v] = (c1 + c0 * z[v] + c2 * t[v]) * term;
+        }
       }
     }
     rescale(next, S, n, sums.data());
@@ -863,41 +887,70 @@ void Oracle::decodeBatch(const std::vector<PairObs>& pairs, const unsigned from,
     std::fill(last, last + plane, 1.0f);
     rescale(last, S, n, sums.data());
   }
-  float* vec = scratchA.data();
-  float* BU = scratchB.data();
-  float* BL = lane1.data();
+  float* __restrict vec = scratchA.data();
+  float* __restrict BU = scratchB.data();
+  float* __restrict BL = lane1.data();
   for (long p = len - 2; p >= 0; --p) {
     const float dist = roundMorgans(genPos[from + p + 1] - genPos[from + p], 2, 1e-10f);
     const float* Bv = dq.B.at(dist).data();
     const float* Uv = dq.U.at(dist).data();
     const float* Rv = dq.RR.at(dist).data();
     const float* Dv = dq.D.at(dist).data();
-    const float* lastBeta = &beta[(p + 1) * plane];
-    float* cur = &beta[p * plane];
+    const float* __restrict lastBeta = &beta[(p + 1) * plane];
+    float* __restrict cur = &beta[p * plane];
+    const float* __restrict z = &isZero[(p + 1) * n];
+    const float* __restrict t = &isTwo[(p + 1) * n];
+    const float* E1 = &e1[(from + p + 1) * static_cast<size_t>(S)];
+    const float* E0 = &e0m1[(from + p + 1) * static_cast<size_t>(S)];
+    const float* E2 = &e2m0[(from + p + 1) * static_cast<size_t>(S)];
     // ref: HMM.cpp:957-964
     for (int k = 0; k < S; ++k) {
-      emission(p + 1, k);
+      const float c1 = E1[k], c0 = E0[k], c2 = E2[k];
+      const float* __restrict lb = lastBeta + static_cast<size_t>(k) * n;
+      float* __restrict o = vec + static_cast<size_t>(k) * n;
+#pragma GCC ivdep
       for (int v = 0; v < n; ++v) {
-        vec[k * n + v] = lastBeta[k * n + v] * em[v];
+        o[v] = lb[v] * (c1 + c0 * z[v] + c2 * t[v]);
       }
     }
     // ref: HMM.cpp:986-990
-    std::fill(BU, BU + plane, 0.f);
+    std::fill(BU + static_cast<size_t>(S - 1) * n, BU + static_cast<size_t>(S) * n, 0.f);
     for (int k = S - 2; k >= 0; --k) {
+      const float u = Uv[k], r = Rv[k];
+      float* __restrict o = BU + static_cast<size_t>(k) * n;
+      const float* __restrict up = BU + static_cast<size_t>(k + 1) * n;
+      const float* __restrict vk = vec + static_cast<size_t>(k + 1) * n;
+#pragma GCC ivdep
       for (int v = 0; v < n; ++v) {
-        BU[k * n + v] = Uv[k] * vec[(k + 1) * n + v] + Rv[k] * BU[(k + 1) * n + v];
+        o[v] = u * vk[v] + r * up[v];
       }
     }
     // ref: HMM.cpp:1008-1016
     std::fill(BL, BL + n, 0.f);
     for (int k = 0; k < S; ++k) {
-      for (int v = 0; v < n; ++v) {
-        if (k) {
-          BL[v] += Bv[k - 1] * vec[(k - 1) * n + v];
+      if (k) {
+        const float bk = Bv[k - 1];
+        const float* __restrict vm = vec + static_cast<size_t>(k - 1) * n;
+#pragma GCC ivdep
+        for (int v = 0; v < n; ++v) {
+          BL[v] += bk * vm[v];
         }
-        // NO_SSE build: (BL + D*vec) + BU (ref: HMM.cpp:1014); SIMD builds: BL + (D*vec + BU) (ref: HMM.cpp:1036-1037)
-        cur[k * n + v] = params.simdFlavor ? BL[v] + (Dv[k] * vec[k * n + v] + BU[k * n + v])
-                                           : BL[v] + Dv[k] * vec[k * n + v] + BU[k * n + v];
+      }
+      const float dk = Dv[k];
+      const float* __restrict vk = vec + static_cast<size_t>(k) * n;
+      const float* __restrict bu = BU + static_cast<size_t>(k) * n;
+      float* __restrict o = cur + static_cast<size_t>(k) * n;
+      // NO_SSE build: (BL + D*vec) + BU (ref: HMM.cpp:1014); SIMD builds: BL + (D*vec + BU) (ref: HMM.cpp:1036-1037)
+      if (params.simdFlavor) {
+#pragma GCC ivdep
+        for (int v = 0; v < n; ++v) {
+          o[v] = BL[v] + (dk * vk[v] + bu[v]);
+        }
+      } else {
+#pragma GCC ivdep
+        for (int v = 0; v < n; ++v) {
+          o[v] = BL[v] + dk * vk[v] + bu[v];
+        }
       }
     }
     rescale(cur, S, n, sums.data());
@@ -905,13 +958,17 @@ void Oracle::decodeBatch(const std::vector<PairObs>& pairs, const unsigned from,
 
   // ---- combine.  ref: HMM.cpp:669-692 (NO_SSE: exact reciprocal)
   for (long p = 0; p < len; ++p) {
-    float* a = &posterior[p * plane];
-    const float* b = &beta[p * plane];
+    float* __restrict a = &posterior[p * plane];
+    const float* __restrict b = &beta[p * plane];
+    float* __restrict sm = sums.data();
     std::fill(sums.begin(), sums.end(), 0.f);
     for (int k = 0; k < S; ++k) {
+      float* __restrict ak = a + static_cast<size_t>(k) * n;
+      const float* __restrict bk = b + static_cast<size_t>(k) * n;
+#pragma GCC ivdep
       for (int v = 0; v < n; ++v) {
-        a[k * n + v] *= b[k * n + v];
-        sums[v] += a[k * n + v];
+        ak[v] *= bk[v];
+        sm[v] += ak[v];
       }
     }
     for (int v = 0; v < n; ++v) {
@@ -920,8 +977,10 @@ void Oracle::decodeBatch(const std::vector<PairObs>& pairs, const unsigned from,
       sums[v] = params.simdFlavor ? _mm_cvtss_f32(_mm_rcp_ss(_mm_set_ss(sums[v]))) : 1.0f / sums[v];
     }
     for (int k = 0; k < S; ++k) {
+      float* __restrict ak = a + static_cast<size_t>(k) * n;
+#pragma GCC ivdep
       for (int v = 0; v < n; ++v) {
-        a[k * n + v] *= sums[v];
+        ak[v] *= sm[v];
       }
     }
   }

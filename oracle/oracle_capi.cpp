@@ -2,6 +2,10 @@
 // cpu_baseline).  See oracle.hpp for the scope rules.
 #include "oracle.hpp"
 
+#include <atomic>
+#include <xmmintrin.h>
+#include <thread>
+
 #include <cstring>
 #include <exception>
 #include <string>
@@ -176,6 +180,67 @@ int fo_get_transition(void* h, float key, float* out)
   std::memcpy(out + 2 * S, o->dq.U.at(key).data(), S * sizeof(float));
   std::memcpy(out + 3 * S, o->dq.RR.at(key).data(), S * sizeof(float));
   return 0;
+}
+
+
+// Decodes the first nPairs pairs of the job's all-pairs enumeration (ref: HMM.cpp:311-357) in reference batches over the
+// whole sequence, segment calling included, on `threads` host threads; returns the pair-sites processed (the CPU
+// baseline of bench.py).  Enumeration of the whole job is avoided: only the needed prefix is generated.
+double fo_decode_sample(void* h, long nPairs, int threads)
+{
+  double pairSites = -1.0;
+  guarded([&] {
+    auto* o = static_cast<fo::Oracle*>(h);
+    std::vector<fo::PairObs> pairs;
+    const unsigned N = static_cast<unsigned>(o->famId.size());
+    for (unsigned i = 0; i < N && static_cast<long>(pairs.size()) < nPairs; ++i) {
+      for (unsigned j = 0; j < i; ++j) {
+        for (int iHap = 1; iHap <= 2; ++iHap) {
+          for (int jHap = 1; jHap <= 2; ++jHap) {
+            pairs.push_back(fo::PairObs{jHap, j, iHap, i});
+          }
+        }
+      }
+      pairs.push_back(fo::PairObs{1, i, 2, i});
+    }
+    if (static_cast<long>(pairs.size()) > nPairs) {
+      pairs.resize(static_cast<size_t>(nPairs));
+    }
+    const std::vector<fo::Batch> batches = o->makeBatches(pairs, nullptr);
+    std::atomic<long> next{0};
+    std::vector<size_t> found(std::max(1, threads), 0);
+    auto worker = [&](const int t) {
+      std::vector<float> posterior;
+      std::vector<fo::Segment> segs;
+      for (long b = next++; b < static_cast<long>(batches.size()); b = next++) {
+        o->decodeBatch(batches[b].pairs, batches[b].from, batches[b].to, posterior);
+        segs.clear();
+        o->callSegments(batches[b], static_cast<uint32_t>(b), posterior, segs);
+        found[t] += segs.size();
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) {
+      pool.emplace_back(worker, t);
+    }
+    worker(0);
+    for (auto& t : pool) {
+      t.join();
+    }
+    pairSites = 0.0;
+    for (const auto& b : batches) {
+      pairSites += static_cast<double>(b.pairs.size()) * (b.to - b.from);
+    }
+  });
+  return pairSites;
+}
+
+// timing experiment only: flush-to-zero / denormals-are-zero on the calling thread
+void fo_set_ftz(int on)
+{
+  unsigned csr = _mm_getcsr();
+  csr = on ? (csr | 0x8040u) : (csr & ~0x8040u);
+  _mm_setcsr(csr);
 }
 
 // whole FastSMC::run; returns #records or -1

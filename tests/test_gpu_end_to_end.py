@@ -1,0 +1,145 @@
+"""End-to-end GPU parity through the reference-facing interface (pyASMC: DecodingParams -> FastSMC.run / ASMC.decodePairs)
+against the CPU oracle on the reference's example data set, in the reference's own regression configurations
+(ASMC_SRC/TESTS/test_fastsmc_regression.cpp:32-160)."""
+import gzip
+
+import numpy as np
+import pytest
+
+from conftest import ASMC_EXAMPLE, DQ_69, FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, REGRESSION_PARAMS
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def asmc():
+    from fastsmc_b200 import asmc as mod
+    return mod
+
+
+def _params(asmc, out, **kw):
+    p = asmc.DecodingParams()
+    p.verbose = False
+    p.inFileRoot = FASTSMC_EXAMPLE
+    p.decodingQuantFile = FASTSMC_EXAMPLE_DQ
+    p.outFileRoot = out
+    p.decodingModeString = "array"
+    p.foldData = True
+    p.usingCSFS = True
+    p.FastSMC = True
+    p.hashing = True
+    for k, v in dict(REGRESSION_PARAMS, **kw).items():
+        setattr(p, k, v)
+    p.validateParamsFastSMC()
+    return p
+
+
+def _lines(path):
+    with gzip.open(path, "rt") as f:
+        return f.read().splitlines()
+
+
+CASES = {"hashing": dict(hashing=True), "no_hashing_job7of9": dict(hashing=False, jobInd=7, jobs=9)}
+
+
+@pytest.mark.parametrize("case", list(CASES))
+def test_fastsmc_run_exact_mode_output_identical_to_oracle(asmc, oracle_mod, tmp_path, case):
+    """FastSMC.run() with exactArithmetic writes the same .ibd.gz text, line for line, as the oracle's NO_SSE flavour:
+    GPU seeding + host order replay + GPU decode + host formatting == the reference pipeline."""
+    kw = CASES[case]
+    p = _params(asmc, str(tmp_path / "gpu"), exactArithmetic=True, **kw)
+    f = asmc.FastSMC(p)
+    f.run()
+    got = _lines(f"{p.outFileRoot}.{p.jobInd}.{p.jobs}.FastSMC.ibd.gz")
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), **kw, **REGRESSION_PARAMS)
+    ref_path = str(tmp_path / "oracle.ibd.gz")
+    n = o.run(ref_path)
+    want = _lines(ref_path)
+    assert len(got) == len(want) == n
+    assert got == want
+
+
+def test_fastsmc_run_fast_mode_within_tolerance(asmc, oracle_mod, tmp_path):
+    """Default (FMA) arithmetic: identical segment boundaries on this data set, score / posterior mean within 1e-4."""
+    p = _params(asmc, str(tmp_path / "gpu"))
+    f = asmc.FastSMC(p)
+    f.run()
+    got = [l.split("\t") for l in _lines(f"{p.outFileRoot}.1.1.FastSMC.ibd.gz")]
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, **REGRESSION_PARAMS)
+    ref_path = str(tmp_path / "oracle.ibd.gz")
+    o.run(ref_path)
+    want = [l.split("\t") for l in _lines(ref_path)]
+    assert [g[:9] for g in got] == [w[:9] for w in want]
+    g = np.array([[float(x) for x in r[9:12]] for r in got])
+    w = np.array([[float(x) for x in r[9:12]] for r in want])
+    np.testing.assert_allclose(g, w, rtol=1e-4)
+
+
+def test_seeding_candidate_set_bit_exact(asmc, oracle_mod, tmp_path):
+    """GPU seeding: the candidate multiset (hapA, hapB, from, to) equals the oracle's; in reference-order mode the
+    sequence is identical too; in canonical mode it is sorted by (end word, hapA, hapB)."""
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, **REGRESSION_PARAMS)
+    want = o.seed().astype(np.int64)
+    for reference_order in (True, False):
+        p = _params(asmc, str(tmp_path / f"gpu{int(reference_order)}"), referenceCandidateOrder=reference_order)
+        f = asmc.FastSMC(p)
+        f.setKeepCandidates(True)
+        f.run()
+        got = f.getCandidates().astype(np.int64)
+        st = f.getSeedingStats()
+        assert st.candidates == len(want) == len(got)
+        assert st.device.numWords == o.sites // 64 and st.device.pairVisits > st.device.numStarts > 0
+        if reference_order:
+            assert np.array_equal(got, want)
+        else:
+            key = lambda a: np.lexsort((a[:, 1], a[:, 0], a[:, 3]))
+            assert np.array_equal(got, want[key(want)])
+            assert np.array_equal(got, got[key(got)])
+
+
+def test_binary_output_round_trip(asmc, tmp_path):
+    """--bin output read back with BinaryDataReader gives the text output's records (ref: HMM.cpp:1147-1175)."""
+    p = _params(asmc, str(tmp_path / "txt"), exactArithmetic=True)
+    asmc.FastSMC(p).run()
+    text = _lines(f"{p.outFileRoot}.1.1.FastSMC.ibd.gz")
+    q = _params(asmc, str(tmp_path / "bin"), exactArithmetic=True, BIN_OUT=True)
+    asmc.FastSMC(q).run()
+    r = asmc.BinaryDataReader(f"{q.outFileRoot}.1.1.FastSMC.bibd.gz")
+    out = []
+    while r.moreLinesInFile():
+        out.append(r.getNextLine().toString())
+    assert len(out) == len(text)
+    assert [l.split("\t")[:9] for l in out] == [l.split("\t")[:9] for l in text]
+    a = np.array([[float(x) for x in l.split("\t")[9:]] for l in out])
+    b = np.array([[float(x) for x in l.split("\t")[9:]] for l in text])
+    np.testing.assert_allclose(a, b, rtol=2e-7)  # the binary score is narrowed to float before printing
+
+
+def test_asmc_decode_pairs_per_site_outputs(asmc, oracle_mod):
+    """ASMC.decodePairs (ASMC_SRC/TESTS/test_ASMC.cpp:45-66 shape): per-site posterior mean and MAP of chosen
+    haplotype pairs vs the oracle, bit-exact in exact mode, 1e-4 otherwise."""
+    a_idx, b_idx = [1, 2, 3, 17, 40], [2, 3, 4, 90, 41]
+    for exact in (True, False):
+        p = asmc.DecodingParams(ASMC_EXAMPLE, DQ_69, "/tmp/fsmc_asmc_test", 1, 1, "array", False, True, False, False, 0.0,
+                                False, True, False, "", False, True)
+        p.useKnownSeed = True
+        p.exactArithmetic = exact
+        p.verbose = False
+        m = asmc.ASMC(p)
+        m.decodePairs(a_idx, b_idx, False, False, True, True)
+        res = m.get_ref_of_results()
+        o = oracle_mod.Oracle(ASMC_EXAMPLE, DQ_69, "/tmp/x", hashing=False, FastSMC=False, asmcMode=True, batchSize=64,
+                              useKnownSeed=True)
+        mean, mp, _ = o.decode_summary(np.array(a_idx), np.array(b_idx))
+        got_mean, got_map = np.array(res.per_pair_posterior_means), np.array(res.per_pair_MAPs)
+        assert got_mean.shape == mean.shape == (5, o.sites)
+        assert [t[0] for t in res.per_pair_indices] == a_idx and [t[2] for t in res.per_pair_indices] == b_idx
+        assert res.per_pair_indices[0][1].endswith("#2") and res.per_pair_indices[0][3].endswith("#1")
+        if exact:
+            assert np.array_equal(got_mean.view(np.uint32), mean.view(np.uint32))
+            assert np.array_equal(got_map, mp)
+        else:
+            np.testing.assert_allclose(got_mean, mean, rtol=1e-4)
+            assert (got_map != mp).mean() < 1e-3
+        assert np.array_equal(np.array(res.min_posterior_means), got_mean.min(axis=0))
+        assert np.array_equal(np.array(res.argmin_posterior_means), got_mean.argmin(axis=0))
