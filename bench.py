@@ -206,7 +206,9 @@ def main():
     S, L = tables["emission1"].shape[1], data.sites
 
     ctx = N.Context(local)
-    stream = torch.cuda.current_stream()
+    # a real (non-default) torch stream: handle 0 would mean "the context's own stream" to fsmc_ctx_set_stream
+    stream = torch.cuda.Stream(device=local)
+    torch.cuda.set_stream(stream)
     ctx.set_stream(stream.cuda_stream)
     ctx.set_model(**tables)
     ctx.set_haplotypes(data.hapBits, L)

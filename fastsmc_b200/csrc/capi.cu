@@ -9,6 +9,7 @@
 #include <vector>
 
 #include "decode_kernels.cuh"
+#include "decode_fast.cuh"
 #include "seed_kernels.cuh"
 
 namespace
@@ -74,7 +75,8 @@ struct fsmc_ctx {
   DevBuf<float> siteRows, prior, expTimes, colRatios;
   DevBuf<uint64_t> haps;
   long long numHaps = 0;
-  DevBuf<float> scratch;
+  DevBuf<float> scratch, accScratch;
+  std::vector<float> hostPrior, hostExpTimes, hostColRatios;
   long long sites = 0;
   // seeding scratch (fsmc_seed)
   DevBuf<uint64_t> seedKeysT;
@@ -108,6 +110,7 @@ struct fsmc_plan {
   long long scratchPerWarp = 0;
   bool launched = false;
   int launches = 0;
+  bool fast = false;  // decodeFastKernel (decode_fast.cuh)
 };
 
 namespace
@@ -142,6 +145,37 @@ KernelChoice chooseKernel(const int S, const unsigned flags)
   }
   return exact ? KernelChoice{fsmc::decodeTilesKernel<0, 2, true, 128, 1>, 0, 2, 128}
                : KernelChoice{fsmc::decodeTilesKernel<0, 2, false, 128, 1>, 0, 2, 128};
+}
+
+// The production kernel (decode_fast.cuh) exists for the state counts whose two state vectors fit the register file.
+typedef void (*FastKernelFn)(const fsmc::FastModel, const DecodeArgs);
+constexpr int kFastDepth = 2, kFastRescale = 4;
+struct FastChoice {
+  FastKernelFn fn = nullptr;
+  int Spad = 0;
+  int threads = 0;
+  bool acc = false;
+};
+// Without per-segment age estimates 8 warps (2 CTAs of 4) fit an SM; the accumulators of FSMC_SEG_AGE cost 8.6 KB of
+// shared memory per warp, which leaves room for 7 warps (1 CTA).
+FastChoice chooseFastKernel(const int S, const unsigned flags)
+{
+  if ((flags & (FSMC_EXACT | FSMC_GENERIC_KERNEL)) || S > fsmc::kMaxParamStates) {
+    return {};
+  }
+  const bool acc = (flags & FSMC_SEG_AGE) && (flags & FSMC_CALL_SEGMENTS);
+  if (S == 69) {
+    return acc ? FastChoice{fsmc::decodeFastKernel<69, kFastDepth, kFastRescale, true, 128, 2>, 72, 128, true}
+               : FastChoice{fsmc::decodeFastKernel<69, kFastDepth, kFastRescale, false, 128, 2>, 72, 128, false};
+  }
+  return {};
+}
+size_t fastSmemBytes(const FastChoice& fc, const int S)
+{
+  const size_t warps = fc.threads / 32;
+  return warps * (kFastDepth * (static_cast<size_t>(fc.Spad) * 32 * 4 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4) +
+                  0 * static_cast<size_t>(S)) +
+         warps * 2 * kFastDepth * sizeof(uint64_t);
 }
 
 size_t smemPerWarp(const DeviceModel& m, const int mode, const unsigned flags)
@@ -286,6 +320,9 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
     std::copy(src, src + S, pad.begin());
     return cudaMemcpyAsync(dst, pad.data(), Spad * sizeof(float), cudaMemcpyHostToDevice, st);
   };
+  ctx->hostPrior.assign(mdl->initialStateProb, mdl->initialStateProb + S);
+  ctx->hostExpTimes.assign(mdl->expectedTimes, mdl->expectedTimes + S);
+  ctx->hostColRatios.assign(mdl->columnRatios, mdl->columnRatios + S);
   FSMC_CUDA(upPad(ctx->prior.p, mdl->initialStateProb));
   FSMC_CUDA(cudaStreamSynchronize(st));
   FSMC_CUDA(upPad(ctx->expTimes.p, mdl->expectedTimes));
@@ -455,23 +492,32 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   // ---- launch geometry --------------------------------------------------------------------------
   const KernelChoice kc = chooseKernel(m.S, flags);
-  plan->statesKernel = kc.statesKernel;
+  const FastChoice fc = chooseFastKernel(m.S, flags);
+  plan->fast = fc.fn != nullptr;
+  plan->statesKernel = plan->fast ? m.S : kc.statesKernel;
   plan->mode = kc.mode;
-  int warpsPerBlock = kc.threads / 32;
-  const size_t perWarp = smemPerWarp(m, kc.mode, flags);
+  int warpsPerBlock = (plan->fast ? fc.threads : kc.threads) / 32;
   const size_t smemLimit = ctx->prop.sharedMemPerBlockOptin;
-  while (warpsPerBlock > 1 && perWarp * warpsPerBlock > smemLimit) {
-    warpsPerBlock /= 2;
-  }
-  if (perWarp * warpsPerBlock > smemLimit) {
-    return fail(FSMC_E_INVALID, "fsmc_plan_create: %d states need %zu bytes of shared memory per warp (limit %zu)", m.S,
-                perWarp, smemLimit);
-  }
-  plan->threads = warpsPerBlock * 32;
-  plan->smemBytes = perWarp * warpsPerBlock;
-  FSMC_CUDA(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
   int blocksPerSm = 0;
-  FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kc.fn, plan->threads, plan->smemBytes));
+  if (plan->fast) {
+    plan->threads = fc.threads;
+    plan->smemBytes = fastSmemBytes(fc, m.S);
+    FSMC_CUDA(cudaFuncSetAttribute(fc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
+    FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, fc.fn, plan->threads, plan->smemBytes));
+  } else {
+    const size_t perWarp = smemPerWarp(m, kc.mode, flags);
+    while (warpsPerBlock > 1 && perWarp * warpsPerBlock > smemLimit) {
+      warpsPerBlock /= 2;
+    }
+    if (perWarp * warpsPerBlock > smemLimit) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_create: %d states need %zu bytes of shared memory per warp (limit %zu)", m.S,
+                  perWarp, smemLimit);
+    }
+    plan->threads = warpsPerBlock * 32;
+    plan->smemBytes = perWarp * warpsPerBlock;
+    FSMC_CUDA(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
+    FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kc.fn, plan->threads, plan->smemBytes));
+  }
   if (blocksPerSm < 1) {
     return fail(FSMC_E_CUDA, "fsmc_plan_create: kernel does not fit on an SM (threads=%d smem=%zu)", plan->threads,
                 plan->smemBytes);
@@ -482,7 +528,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   // backward-sweep scratch: one slab of maxLen*S*32 floats per resident warp.  Shrink the grid if
   // the slabs would not fit in 85% of the free memory.
-  plan->scratchPerWarp = maxLen * m.S * 32;
+  plan->scratchPerWarp = maxLen * (plan->fast ? fc.Spad : m.S) * 32;
   const size_t slabBytes = static_cast<size_t>(plan->scratchPerWarp) * sizeof(float);
   if (slabBytes > 0) {
     size_t freeB = 0, totalB = 0;
@@ -500,6 +546,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     }
     FSMC_CUDA(ctx->scratch.ensure(static_cast<size_t>(blocks) * warpsPerBlock * plan->scratchPerWarp));
   }
+
   plan->blocks = static_cast<int>(blocks);
   guard.keep = true;
   *out = plan;
@@ -539,8 +586,19 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
     a.scratch = ctx->scratch.p;
     a.scratchPerWarp = plan->scratchPerWarp;
     a.tileCounter = plan->counters.p + 1;
-    const KernelChoice kc = chooseKernel(m.S, plan->flags);
-    kc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(m, a);
+    a.accScratch = nullptr;
+    if (plan->fast) {
+      fsmc::FastModel fm{};
+      fm.base = m;
+      std::copy(ctx->hostColRatios.begin(), ctx->hostColRatios.end(), fm.colRatios);
+      std::copy(ctx->hostExpTimes.begin(), ctx->hostExpTimes.end(), fm.expTimes);
+      std::copy(ctx->hostPrior.begin(), ctx->hostPrior.end(), fm.prior);
+      const FastChoice fc = chooseFastKernel(m.S, plan->flags);
+      fc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(fm, a);
+    } else {
+      const KernelChoice kc = chooseKernel(m.S, plan->flags);
+      kc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(m, a);
+    }
     FSMC_CUDA(cudaGetLastError());
     plan->launches = 1;
   }

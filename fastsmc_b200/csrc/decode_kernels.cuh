@@ -66,6 +66,7 @@ struct DecodeArgs {
   long long siteStride;
   float* scratch;              // beta slabs
   long long scratchPerWarp;    // floats per warp slab
+  float* accScratch;           // fast kernel: per-warp [S][32] per-state segment sums
   unsigned long long* tileCounter;
 };
 

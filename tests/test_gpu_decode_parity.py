@@ -152,3 +152,71 @@ def test_no_hashing_job_exact(oracle_mod):
     assert np.array_equal(seg["prob"].view(np.uint32), floats[:, 0].copy().view(np.uint32))
     assert np.array_equal(seg["postMean"].view(np.uint32), floats[:, 1].copy().view(np.uint32))
     assert np.array_equal(seg["mapState"], ints[:, 6])
+
+
+# ---- 69-state decoding quantities (30-100-2000, the UKBB-style table of the synthetic benchmarks): this is the state
+# count the production kernel (decode_fast.cuh) is specialised for --------------------------------------------------
+
+
+@pytest.fixture(scope="module")
+def synthetic69(oracle_mod, tmp_path_factory):
+    from conftest import DQ_69
+    from fastsmc_b200 import synth
+    root = str(tmp_path_factory.mktemp("syn69") / "syn")
+    synth.dataset(root, 400, 3000, 9_000_000, 1, 777)
+    o = oracle_mod.Oracle(root, DQ_69, "/tmp/fsmc_test69", hashing=False, time=50, noConditionalAgeEstimates=True,
+                          doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
+    ctx = context_from_oracle(o, oracle_mod)
+    return o, ctx
+
+
+def test_fast_kernel_per_site_outputs_69_states(synthetic69):
+    """Production kernel (FMA, rescaling every 4th site, bulk-copy ring): per-site posterior mean, IBD probability and MAP
+    within the north-star tolerance of the oracle; ragged windows and a partially filled tile included."""
+    from fastsmc_b200 import _native as N
+    o, ctx = synthetic69
+    rng = np.random.default_rng(5)
+    a, b = _pairs(rng, 70, o.num_haps)  # 3 tiles, the last one with 6 pairs
+    for frm, to in ((0, o.sites), (517, 1203), (2999, 3000), (0, 2)):
+        mean, mp, ibd = o.decode_summary(a, b, frm, to)
+        nb = (len(a) + 31) // 32
+        tiles = ctx.make_tiles(a, b, windows=[[frm, to]] * nb, sites=o.sites)
+        r = ctx.decode(tiles, N.SITE_MEAN | N.SITE_MAP | N.SITE_IBD)
+        assert r.stats.statesKernel == 69
+        rows = tiles["rows"]
+        np.testing.assert_allclose(r.site_mean[rows, :to - frm], mean, rtol=REL_TOL)
+        np.testing.assert_allclose(r.site_ibd[rows, :to - frm], ibd, rtol=REL_TOL, atol=1e-12)
+        assert (r.site_map[rows, :to - frm] != mp).mean() < 2e-3
+
+
+def test_fast_kernel_segments_69_states(synthetic69):
+    """Whole all-pairs job slice through the production kernel vs the oracle: same segments (a boundary may move only
+    where the IBD probability is within tolerance of a threshold), sums and age estimates within 1e-4."""
+    from fastsmc_b200 import _native as N
+    o, ctx = synthetic69
+    n = o.run("/tmp/fsmc_test69_oracle.ibd.gz")
+    ints, floats = o.segments()
+    H = o.num_haps
+    a, b = [], []
+    for i in range(H // 2):
+        for j in range(i):
+            for ih in (0, 1):
+                for jh in (0, 1):
+                    a.append(2 * j + jh)
+                    b.append(2 * i + ih)
+        a.append(2 * i)
+        b.append(2 * i + 1)
+    tiles = ctx.make_tiles(np.array(a), np.array(b), sites=o.sites)
+    r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE, segment_capacity=1 << 20)
+    seg = r.segments
+    assert r.stats.statesKernel == 69
+    want = {(int(i[0]) * 32 + int(i[1]), int(i[4]), int(i[5])): f for i, f in zip(ints, floats)}
+    got = {(int(s["pair"]), int(s["posStart"]), int(s["posEnd"])): s for s in seg}
+    common = set(want) & set(got)
+    # identical segment lists up to threshold ties
+    assert len(common) >= 0.999 * max(len(want), len(got)) and abs(len(seg) - n) <= 0.001 * n + 2
+    w = np.array([want[k] for k in sorted(common)])
+    g = np.array([[got[k]["prob"], got[k]["postMean"], got[k]["mapTime"]] for k in sorted(common)])
+    np.testing.assert_allclose(g[:, 0], w[:, 0], rtol=REL_TOL)
+    np.testing.assert_allclose(g[:, 1], w[:, 1], rtol=REL_TOL)
+    assert (g[:, 2] != w[:, 2]).mean() < 5e-3
