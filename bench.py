@@ -306,7 +306,7 @@ def main():
                              "through HBM (>> 126 MB L2)", "parallelism": f"{world} independent jobs, one per GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
-                         "kernel": "decodeTilesKernel", "kernel_ms": kernel_ms,
+                         "kernel": "decodeFastKernel<69>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_pair_site": bytes_per_pair_site},
             "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
                               "flops_per_pair_site": FLOPS_PER_PAIR_SITE_STATE * S,
