@@ -21,6 +21,7 @@ SITE_MAP = 0x8
 SITE_IBD = 0x10
 EXACT = 0x20
 GENERIC_KERNEL = 0x40
+WIDE_KERNEL = 0x80
 
 E_OVERFLOW = -4
 
@@ -58,6 +59,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("numSegments", C.c_int64), ("pairSites", C.c_double), ("kernelMs", C.c_float), ("totalMs", C.c_float),
         ("kernelLaunches", C.c_int32), ("statesKernel", C.c_int32), ("scratchBytes", C.c_int64),
+        ("narrowKernel", C.c_int32), ("reserved", C.c_int32),
     ]
 
 

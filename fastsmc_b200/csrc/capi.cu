@@ -3,6 +3,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
@@ -110,7 +111,8 @@ struct fsmc_plan {
   long long scratchPerWarp = 0;
   bool launched = false;
   int launches = 0;
-  bool fast = false;  // decodeFastKernel (decode_fast.cuh)
+  bool fast = false;  // decodeFastKernel / decodeNarrowKernel (decode_fast.cuh)
+  bool narrow = false;
 };
 
 namespace
@@ -155,15 +157,30 @@ struct FastChoice {
   int Spad = 0;
   int threads = 0;
   bool acc = false;
+  bool narrow = false;      // decodeNarrowKernel: sT+1 floats per pair-site in HBM instead of S
+  int recordQuads = 0;
 };
 // Without per-segment age estimates 8 warps (2 CTAs of 4) fit an SM; the accumulators of FSMC_SEG_AGE cost 8.6 KB of
 // shared memory per warp, which leaves room for 7 warps (1 CTA).
-FastChoice chooseFastKernel(const int S, const unsigned flags)
+FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
 {
+  const int S = m.S;
   if ((flags & (FSMC_EXACT | FSMC_GENERIC_KERNEL)) || S > fsmc::kMaxParamStates) {
     return {};
   }
   const bool acc = (flags & FSMC_SEG_AGE) && (flags & FSMC_CALL_SEGMENTS);
+  // only states below the IBD time threshold are looked at: no beta round trip needed
+  const bool narrow = !(flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP | FSMC_WIDE_KERNEL)) && (!acc || m.ageThreshold <= m.stateThreshold) &&
+                      m.stateThreshold + 1 <= 4 * fsmc::kNarrowMaxQuads;
+  if (S == 69 && narrow) {
+    // 2 CTAs x 4 warps per SM at 255 registers: measured 12.2e9 pair-sites/s vs 10.1e9 at 3 CTAs / 168 registers (spills)
+    const int rq = (m.stateThreshold + 1 + 3) / 4;
+    FastKernelFn fn = rq == 1   ? fsmc::decodeNarrowKernel<69, 1, kFastDepth, kFastRescale, 128, 2>
+                      : rq == 2 ? fsmc::decodeNarrowKernel<69, 2, kFastDepth, kFastRescale, 128, 2>
+                      : rq == 3 ? fsmc::decodeNarrowKernel<69, 3, kFastDepth, kFastRescale, 128, 2>
+                                : fsmc::decodeNarrowKernel<69, 4, kFastDepth, kFastRescale, 128, 2>;
+    return FastChoice{fn, 72, 128, false, true, rq};
+  }
   if (S == 69) {
     return acc ? FastChoice{fsmc::decodeFastKernel<69, kFastDepth, kFastRescale, true, 128, 2>, 72, 128, true}
                : FastChoice{fsmc::decodeFastKernel<69, kFastDepth, kFastRescale, false, 128, 2>, 72, 128, false};
@@ -173,6 +190,10 @@ FastChoice chooseFastKernel(const int S, const unsigned flags)
 size_t fastSmemBytes(const FastChoice& fc, const int S)
 {
   const size_t warps = fc.threads / 32;
+  if (fc.narrow) {
+    return warps * kFastDepth * (static_cast<size_t>(fsmc::kNarrowMaxQuads) * 32 * 16 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4) +
+           warps * 2 * kFastDepth * sizeof(uint64_t);
+  }
   return warps * (kFastDepth * (static_cast<size_t>(fc.Spad) * 32 * 4 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4) +
                   0 * static_cast<size_t>(S)) +
          warps * 2 * kFastDepth * sizeof(uint64_t);
@@ -492,9 +513,10 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   // ---- launch geometry --------------------------------------------------------------------------
   const KernelChoice kc = chooseKernel(m.S, flags);
-  const FastChoice fc = chooseFastKernel(m.S, flags);
+  const FastChoice fc = chooseFastKernel(m, flags);
   plan->fast = fc.fn != nullptr;
   plan->statesKernel = plan->fast ? m.S : kc.statesKernel;
+  plan->narrow = fc.narrow;
   plan->mode = kc.mode;
   int warpsPerBlock = (plan->fast ? fc.threads : kc.threads) / 32;
   const size_t smemLimit = ctx->prop.sharedMemPerBlockOptin;
@@ -528,7 +550,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   // backward-sweep scratch: one slab of maxLen*S*32 floats per resident warp.  Shrink the grid if
   // the slabs would not fit in 85% of the free memory.
-  plan->scratchPerWarp = maxLen * (plan->fast ? fc.Spad : m.S) * 32;
+  plan->scratchPerWarp = maxLen * (plan->fast ? (fc.narrow ? fc.recordQuads * 4 : fc.Spad) : m.S) * 32;
   const size_t slabBytes = static_cast<size_t>(plan->scratchPerWarp) * sizeof(float);
   if (slabBytes > 0) {
     size_t freeB = 0, totalB = 0;
@@ -593,7 +615,7 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
       std::copy(ctx->hostColRatios.begin(), ctx->hostColRatios.end(), fm.colRatios);
       std::copy(ctx->hostExpTimes.begin(), ctx->hostExpTimes.end(), fm.expTimes);
       std::copy(ctx->hostPrior.begin(), ctx->hostPrior.end(), fm.prior);
-      const FastChoice fc = chooseFastKernel(m.S, plan->flags);
+      const FastChoice fc = chooseFastKernel(m, plan->flags);
       fc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(fm, a);
     } else {
       const KernelChoice kc = chooseKernel(m.S, plan->flags);
@@ -677,6 +699,7 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
     }
     stats->kernelLaunches = plan->launches;
     stats->statesKernel = plan->statesKernel;
+    stats->narrowKernel = plan->narrow ? 1 : 0;
     stats->scratchBytes = static_cast<int64_t>(plan->scratchPerWarp) * sizeof(float) * plan->blocks * (plan->threads / 32);
   }
   plan->launched = false;

@@ -96,22 +96,492 @@ __device__ __forceinline__ float f4(const float4& v, const int j)
   return j == 0 ? v.x : (j == 1 ? v.y : (j == 2 ? v.z : v.w));
 }
 
+
+// ---- the two recurrences on register-resident state vectors; coefficient row in shared memory ---------------------
+// row = [E(hom-major) | E(het) | E(hom-minor) | D | B | U | RR], each Spad floats (buildSiteRowsKernel).
+// Both steps read one vector and write the OTHER one ("ping-pong"): every element's last read is the instruction that
+// overwrites its partner, so the unrolled site loop (two sites per trip, roles swapped) needs no register moves at its
+// back edge (the in-place form cost 77 MOVs per warp-site, profiles/r1_v3_*).
+
+// x: beta(p+1) on entry (destroyed); y: unscaled beta(p) on return.  ref: HMM.cpp:957-1016
+template <int S> __device__ __forceinline__ void backwardStep(float (&x)[S], float (&y)[S], const float* row, const int cls)
+{
+  constexpr int SQ = (S + 3) / 4, Spad = SQ * 4;
+  const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
+  const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
+  const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
+  const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
+  const float4* Rr = reinterpret_cast<const float4*>(row + 6 * Spad);
+  // vec = beta(p+1) * emission(p+1), in place in x
+#pragma unroll
+  for (int q = 0; q < SQ; ++q) {
+    const float4 e4 = E[q];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int k = 4 * q + i;
+      if (k < S) {
+        x[k] *= f4(e4, i);
+      }
+    }
+  }
+  // y[k] = BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
+  {
+    float bu = 0.f;
+#pragma unroll
+    for (int q = SQ - 1; q >= 0; --q) {
+      const float4 u4 = Ur[q];
+      const float4 r4 = Rr[q];
+#pragma unroll
+      for (int i = 3; i >= 0; --i) {
+        const int k = 4 * q + i;
+        if (k == S - 1) {
+          y[k] = 0.f;
+        } else if (k < S - 1) {
+          bu = fmaf(f4(r4, i), bu, f4(u4, i) * x[k + 1]);
+          y[k] = bu;
+        }
+      }
+    }
+  }
+  // y[k] = beta(p)[k] = BL + D[k] vec[k] + BU[k], BL += B[k-1] vec[k-1]
+  {
+    float bl = 0.f;
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      const float4 d4 = Dr[q];
+      const float4 b4 = Br[q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = 4 * q + i;
+        if (k < S) {
+          y[k] = fmaf(f4(d4, i), x[k], bl) + y[k];
+          bl = fmaf(f4(b4, i), x[k], bl);
+        }
+      }
+    }
+  }
+}
+
+template <int S> __device__ __forceinline__ float sumStates(const float (&a)[S])
+{
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+  for (int k = 0; k < S; k += 4) {
+    s0 += a[k];
+    if (k + 1 < S) s1 += a[k + 1];
+    if (k + 2 < S) s2 += a[k + 2];
+    if (k + 3 < S) s3 += a[k + 3];
+  }
+  return (s0 + s1) + (s2 + s3);
+}
+
+template <int S> __device__ __forceinline__ void scaleStates(float (&a)[S], const float sc)
+{
+#pragma unroll
+  for (int k = 0; k < S; ++k) {
+    a[k] *= sc;
+  }
+}
+
+// x: alpha(p-1) on entry; y: unscaled alpha(p) on return (x is left holding the suffix sums).  Returns
+// sum_k alpha(p-1)[k], the normaliser of the previous site, for free.  ref: HMM.cpp:799-830
+template <int S>
+__device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[S], float (&y)[S], const float* row, const int cls)
+{
+  constexpr int SQ = (S + 3) / 4, Spad = SQ * 4;
+  const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
+  const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
+  const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
+  const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
+  // ascending pass 1: y[k] = AU[k] + D[k] x[k]  with  AU[k] = U[k-1] x[k-1] + colRatio[k-1] AU[k-1]
+  {
+    float au = 0.f;
+#pragma unroll
+    for (int q = 0; q < SQ; ++q) {
+      const float4 d4 = Dr[q];
+      const float4 u4 = Ur[q];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        const int k = 4 * q + i;
+        if (k < S) {
+          y[k] = fmaf(f4(d4, i), x[k], au);
+          au = fmaf(colRatios[k], au, f4(u4, i) * x[k]);
+        }
+      }
+    }
+  }
+  // descending pass 2: run = sum_{j>k} x[j];  y[k] = E[k] (y[k] + B[k] run)
+  float run = 0.f;
+#pragma unroll
+  for (int q = SQ - 1; q >= 0; --q) {
+    const float4 e4 = E[q];
+    const float4 b4 = Br[q];
+#pragma unroll
+    for (int i = 3; i >= 0; --i) {
+      const int k = 4 * q + i;
+      if (k < S) {
+        y[k] = f4(e4, i) * (k < S - 1 ? fmaf(f4(b4, i), run, y[k]) : y[k]);
+        run += x[k];
+      }
+    }
+  }
+  return run;
+}
+
 // -------------------------------------------------------------------------------------------------------------------
+// decodeNarrowKernel: the same sweeps WITHOUT the beta round trip, for requests that only look at the states below the
+// IBD time threshold (segment calling, per-site IBD probability, and age estimates conditioned on TMRCA < threshold,
+// which is FastSMC's default: ageThreshold == stateThreshold, ref: HMM.cpp:101-105).
+//
+// What the consumers need at site t is  sum_{k<sT} alpha_t[k] beta_t[k] / Z_t  with  Z_t = sum_k alpha_t[k] beta_t[k]
+// over ALL states.  For scaled vectors alpha^ = alpha/A_t, beta^ = beta/B_t the full dot product telescopes:
+// Z_t = P(data)/(A_t B_t), hence Z_{t+1} = Z_t * b_t / a_{t+1} with a, b the per-site scale divisors that the sweeps
+// apply anyway.  Z is computed exactly once (at the first site, where the backward sweep ends with all of beta in
+// registers) and carried by that recurrence, so the backward sweep only has to leave a record of 4*RQ floats per
+// pair-site in HBM (beta^[k < sT], zero padding, and b_t in the last slot) instead of S: 16 bytes instead of 276 at
+// S=69, sT<=3.  The kernel becomes issue-bound.
+// -------------------------------------------------------------------------------------------------------------------
+constexpr int kNarrowMaxQuads = 4;  // record = up to 16 floats: sT <= 15
+
+template <int S_T, int RQ, int DEPTH, int RESCALE, int THREADS, int MIN_BLOCKS>
+__global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const FastModel fm, const DecodeArgs args)
+{
+  constexpr int S = S_T;
+  constexpr int SQ = (S + 3) / 4;
+  constexpr int Spad = SQ * 4;
+  constexpr int NR = 4 * RQ - 1;                     // beta entries of a record; entry NR is the scale divisor
+  constexpr uint32_t kRecBytes = RQ * 32 * 16;
+  constexpr size_t kRecFloats = static_cast<size_t>(RQ) * 32 * 4;
+  constexpr uint32_t kRecSlotBytes = kNarrowMaxQuads * 32 * 16;  // slots are sized for the largest record (parking area)
+  constexpr uint32_t kCoefBytes = kRowArrays * Spad * 4;
+  constexpr int kWarps = THREADS / 32;
+  constexpr size_t kWarpBytes = static_cast<size_t>(DEPTH) * (kRecSlotBytes + kCoefBytes);
+  static_assert(S >= 4 * kNarrowMaxQuads && RQ >= 1 && RQ <= kNarrowMaxQuads, "record quads index the state vector");
+
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  const DeviceModel m = fm.base;
+  const int lane = threadIdx.x & 31;
+  const int warp = threadIdx.x >> 5;
+  unsigned char* mine = smemRaw + static_cast<size_t>(warp) * kWarpBytes;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + static_cast<size_t>(kWarps) * kWarpBytes) + warp * 2 * DEPTH;
+  auto recSlot = [&](const int i) { return reinterpret_cast<float4*>(mine + static_cast<size_t>(i) * kRecSlotBytes); };
+  auto coefSlot = [&](const int i) {
+    return reinterpret_cast<const float*>(mine + static_cast<size_t>(DEPTH) * kRecSlotBytes + static_cast<size_t>(i) * kCoefBytes);
+  };
+  if (lane == 0) {
+    for (int i = 0; i < 2 * DEPTH; ++i) {
+      mbarInit(&bars[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncwarp();
+  uint32_t recParity = 0, coefParity = 0;
+
+  const unsigned flags = args.flags;
+  const bool wantSeg = flags & FSMC_CALL_SEGMENTS;
+  const bool wantAge = (flags & FSMC_SEG_AGE) && wantSeg;
+  const int sT = m.stateThreshold;  // <= NR by the host's kernel choice
+  const long long warpGlobal = static_cast<long long>(blockIdx.x) * kWarps + warp;
+  float* slab = args.scratch + warpGlobal * args.scratchPerWarp;
+
+  for (;;) {
+    unsigned long long t = 0;
+    if (lane == 0) {
+      t = atomicAdd(args.tileCounter, 1ull);
+    }
+    t = __shfl_sync(kFull, t, 0);
+    if (static_cast<long long>(t) >= args.numTiles) {
+      break;
+    }
+    const int tile = args.order ? args.order[t] : static_cast<int>(t);
+    const int nPairs = args.tilePairs[tile];
+    const int from = args.tileFrom[tile];
+    const int len = args.tileTo[tile] - from;
+    const int scanFrom = wantSeg ? args.tileScanFrom[tile] : 0;
+    const int scanTo = wantSeg ? args.tileScanTo[tile] : 0;
+    const bool laneActive = lane < nPairs;
+    const int srcLane = laneActive ? lane : nPairs - 1;
+    const uint32_t pair = static_cast<uint32_t>(tile) * 32u + static_cast<uint32_t>(lane);
+    PairBits bits;
+    bits.a = m.haps + static_cast<size_t>(args.hapA[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
+    bits.b = m.haps + static_cast<size_t>(args.hapB[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
+    const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowArrays * Spad;
+
+    float a[S], c[S];
+    float acc[NR];
+#pragma unroll
+    for (int k = 0; k < NR; ++k) {
+      acc[k] = 0.f;
+    }
+
+    // stage (beta^[k < sT], 0.., scale divisor) of window position p and hand it to the copy engine
+    auto storeRecord = [&](const float (&v)[S], const int p, const int bslot, const float divisor) {
+      if (lane == 0) {
+        bulkWaitRead<DEPTH - 1>();
+      }
+      __syncwarp();
+      float4* out = recSlot(bslot);
+#pragma unroll
+      for (int q = 0; q < RQ; ++q) {
+        float w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int k = 4 * q + i;
+          w[i] = k == NR ? divisor : (k < sT ? v[k] : 0.f);
+        }
+        out[q * 32 + lane] = make_float4(w[0], w[1], w[2], w[3]);
+      }
+      fenceProxyAsync();
+      __syncwarp();
+      if (lane == 0) {
+        bulkStore(slab + static_cast<size_t>(p) * kRecFloats, out, kRecBytes);
+        bulkCommit();
+      }
+    };
+
+    // ---- sweep 1: backward.  Step j handles window position len-2-j with the coefficient row of len-1-j ------------
+    {
+      auto prefetchCoef = [&](const int j) {
+        if (lane == 0) {
+          uint64_t* bar = &bars[DEPTH + j % DEPTH];
+          mbarExpectTx(bar, kCoefBytes);
+          bulkLoad(const_cast<float*>(coefSlot(j % DEPTH)), rowBase + static_cast<size_t>(len - 1 - j) * kRowArrays * Spad,
+                   kCoefBytes, bar);
+        }
+      };
+      const int steps = len - 1;
+      for (int j = 0; j < DEPTH && j < steps; ++j) {
+        prefetchCoef(j);
+      }
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        a[k] = 1.f;
+      }
+      storeRecord(a, len - 1, 0, 1.0f);
+      auto step = [&](const int j, float (&x)[S], float (&y)[S]) {
+        const int p = len - 2 - j;
+        const int slot = j % DEPTH;
+        const int cls = bits.cls(from + p + 1);
+        mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
+        coefParity ^= 1u << slot;
+        backwardStep<S>(x, y, coefSlot(slot), cls);
+        __syncwarp();
+        if (j + DEPTH < steps) {
+          prefetchCoef(j + DEPTH);
+        }
+        float divisor = 1.0f;
+        if ((p & (RESCALE - 1)) == 0) {
+          divisor = sumStates<S>(y);
+          scaleStates<S>(y, 1.0f / divisor);
+        }
+        storeRecord(y, p, (j + 1) % DEPTH, divisor);
+      };
+      int j = 0;
+      for (; j + 1 < steps; j += 2) {
+        step(j, a, c);
+        step(j + 1, c, a);
+      }
+      if (j < steps) {
+        step(j, a, c);  // beta^ of the first site ends in c
+      } else {
+#pragma unroll
+        for (int k = 0; k < S; ++k) {
+          c[k] = a[k];
+        }
+      }
+      if (lane == 0) {
+        bulkWaitAll<0>();
+      }
+      __syncwarp();
+    }
+
+    // ---- sweep 2: forward + consumers ---------------------------------------------------------------------------------
+    {
+      auto prefetch = [&](const int p) {
+        if (lane == 0) {
+          const int slot = p % DEPTH;
+          mbarExpectTx(&bars[slot], kRecBytes);
+          bulkLoad(recSlot(slot), slab + static_cast<size_t>(p) * kRecFloats, kRecBytes, &bars[slot]);
+          mbarExpectTx(&bars[DEPTH + slot], kCoefBytes);
+          bulkLoad(const_cast<float*>(coefSlot(slot)), rowBase + static_cast<size_t>(p) * kRowArrays * Spad, kCoefBytes,
+                   &bars[DEPTH + slot]);
+        }
+      };
+      for (int p = 0; p < DEPTH && p < len; ++p) {
+        prefetch(p);
+      }
+      CallerState cs;
+      float Z = 1.f, bPrev = 1.f;
+
+      // consumers of window position p; v = alpha^(p)
+      auto consume = [&](const int p, const float (&v)[S]) {
+        const int site = from + p;
+        const int slot = p % DEPTH;
+        mbarWait(&bars[slot], (recParity >> slot) & 1u);
+        recParity ^= 1u << slot;
+        const float4* R4 = recSlot(slot);
+        float q[4 * RQ];  // alpha^[k] beta^[k] for k < sT (0 above); q[NR] = b_p
+#pragma unroll
+        for (int qq = 0; qq < RQ; ++qq) {
+          const float4 r4 = R4[qq * 32 + lane];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            q[4 * qq + i] = f4(r4, i);
+          }
+        }
+        bPrev = q[NR];
+        float ibdRaw = 0.f;
+#pragma unroll
+        for (int k = 0; k < NR; ++k) {
+          q[k] *= v[k];
+          ibdRaw += q[k];
+        }
+        const float r = 1.0f / Z;
+        const float ibd = ibdRaw * r;
+        if ((flags & FSMC_SITE_IBD) && laneActive) {
+          args.siteIbd[static_cast<size_t>(pair) * args.siteStride + p] = ibd;
+        }
+        const bool inScan = wantSeg && site >= scanFrom && site < scanTo;
+        if (inScan) {
+          int now = -1;
+          if (ibd >= m.thr[0]) {
+            now = 0;
+          } else if (ibd >= m.thr[1]) {
+            now = 1;
+          } else if (ibd >= m.thr[2]) {
+            now = 2;
+          } else if (ibd >= m.thr[3]) {
+            now = 3;
+          }
+          if (!laneActive) {
+            now = -1;
+          }
+          const bool changed = now != cs.level;
+          const bool ending = changed && cs.level >= 0;
+          const bool closing = now >= 0 && site == scanTo - 1;
+          float* park = reinterpret_cast<float*>(recSlot(slot)) + lane;  // drained record slot: [k][32], k < 15
+          if (__any_sync(kFull, ending)) {
+            if (wantAge) {
+#pragma unroll
+              for (int k = 0; k < NR; ++k) {
+                park[k * 32] = acc[k];
+              }
+              __syncwarp();
+            }
+            if (ending) {
+              emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, park, wantAge);
+            }
+            __syncwarp();
+          }
+          if (wantAge) {
+            const float rr = now >= 0 ? r : 0.f;
+            const float keep = changed ? 0.f : 1.f;
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+              acc[k] = fmaf(q[k], rr, keep * acc[k]);
+            }
+          }
+          if (__any_sync(kFull, closing)) {
+            if (wantAge) {
+#pragma unroll
+              for (int k = 0; k < NR; ++k) {
+                park[k * 32] = acc[k];
+              }
+              __syncwarp();
+            }
+            if (closing) {
+              emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, park, wantAge);
+            }
+            __syncwarp();
+          }
+          if (now >= 0) {
+            cs.prob = changed ? ibd : cs.prob + ibd;
+            if (changed) {
+              cs.start = site;
+            }
+            if (closing) {
+              cs.prob = 0.f;
+            }
+          } else {
+            cs.prob = 0.f;
+          }
+          cs.level = now;
+        }
+        __syncwarp();
+        if (p + DEPTH < len) {
+          prefetch(p + DEPTH);
+        }
+      };
+
+      // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
+      {
+        const int cls = bits.cls(from);
+        mbarWait(&bars[DEPTH], coefParity & 1u);
+        coefParity ^= 1u;
+        const float4* E = reinterpret_cast<const float4*>(coefSlot(0) + cls * Spad);
+        float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) {
+          const float4 e4 = E[q];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = 4 * q + i;
+            if (k < S) {
+              a[k] = fm.prior[k] * f4(e4, i);
+            }
+          }
+          z0 = fmaf(a[4 * q], c[4 * q], z0);
+          if (4 * q + 1 < S) z1 = fmaf(a[4 * q + 1], c[4 * q + 1], z1);
+          if (4 * q + 2 < S) z2 = fmaf(a[4 * q + 2], c[4 * q + 2], z2);
+          if (4 * q + 3 < S) z3 = fmaf(a[4 * q + 3], c[4 * q + 3], z3);
+        }
+        Z = (z0 + z1) + (z2 + z3);
+        consume(0, a);
+      }
+      auto step = [&](const int p, float (&x)[S], float (&y)[S]) {
+        const int slot = p % DEPTH;
+        const int cls = bits.cls(from + p);
+        mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
+        coefParity ^= 1u << slot;
+        const float total = forwardStep<S>(fm.colRatios, x, y, coefSlot(slot), cls);
+        float sc = 1.0f;
+        if ((p & (RESCALE - 1)) == 0) {
+          sc = 1.0f / total;
+          scaleStates<S>(y, sc);
+        }
+        Z *= bPrev * sc;  // Z_p = Z_{p-1} * b_{p-1} / a_p
+        consume(p, y);
+      };
+      int p = 1;
+      for (; p + 1 < len; p += 2) {
+        step(p, a, c);
+        step(p + 1, c, a);
+      }
+      if (p < len) {
+        step(p, a, c);
+      }
+    }
+    __syncwarp();
+  }
+}
+
+// -------------------------------------------------------------------------------------------------------------------
+// decodeFastKernel: all states reach the consumers (per-site posterior mean / MAP, age estimates over all states):
+// the backward sweep streams full beta rows through HBM.
 // S_T   : states (compile time), DEPTH: ring depth, RESCALE: sites between rescalings (power of two)
-// -------------------------------------------------------------------------------------------------------------------
 // ACC   : keep per-state segment accumulators (FSMC_SEG_AGE) in registers
+// -------------------------------------------------------------------------------------------------------------------
 template <int S_T, int DEPTH, int RESCALE, bool ACC, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const FastModel fm, const DecodeArgs args)
 {
   constexpr int S = S_T;
   constexpr int SQ = (S + 3) / 4;
   constexpr int Spad = SQ * 4;
-  constexpr uint32_t kBetaBytes = SQ * 32 * 16;              // one site of beta for 32 lanes
-  constexpr uint32_t kCoefBytes = kRowArrays * Spad * 4;     // one site's coefficient row
+  constexpr uint32_t kBetaBytes = SQ * 32 * 16;           // one site of beta for 32 lanes
+  constexpr uint32_t kCoefBytes = kRowArrays * Spad * 4;  // one site's coefficient row
   constexpr size_t kBetaFloats = static_cast<size_t>(SQ) * 32 * 4;
   constexpr int kWarps = THREADS / 32;
-  constexpr uint32_t kAccBytes = 0;  // the accumulators live in registers
-  constexpr size_t kWarpBytes = static_cast<size_t>(DEPTH) * (kBetaBytes + kCoefBytes) + kAccBytes;
+  constexpr size_t kWarpBytes = static_cast<size_t>(DEPTH) * (kBetaBytes + kCoefBytes);
 
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceModel m = fm.base;  // a copy: taking the address of a kernel parameter would move all of fm to local memory
@@ -140,8 +610,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
   const int sT = m.stateThreshold;
   const int nAcc = m.ageThreshold;
   const long long warpGlobal = static_cast<long long>(blockIdx.x) * kWarps + warp;
-  float* slab = args.scratch + warpGlobal * args.scratchPerWarp;                      // beta rows of this warp
-
+  float* slab = args.scratch + warpGlobal * args.scratchPerWarp;  // beta rows of this warp
 
   for (;;) {
     unsigned long long t = 0;
@@ -173,6 +642,26 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
       acc[k] = 0.f;
     }
 
+    // stage the beta row of window position p and hand it to the copy engine
+    auto storeRow = [&](const float (&v)[S], const int p, const int bslot) {
+      if (lane == 0) {
+        bulkWaitRead<DEPTH - 1>();  // the copy that last read this staging slot has drained it
+      }
+      __syncwarp();
+      float4* out = betaSlot(bslot);
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        out[q * 32 + lane] = make_float4(v[4 * q], 4 * q + 1 < S ? v[4 * q + 1] : 0.f, 4 * q + 2 < S ? v[4 * q + 2] : 0.f,
+                                         4 * q + 3 < S ? v[4 * q + 3] : 0.f);
+      }
+      fenceProxyAsync();
+      __syncwarp();
+      if (lane == 0) {
+        bulkStore(slab + static_cast<size_t>(p) * kBetaFloats, out, kBetaBytes);
+        bulkCommit();
+      }
+    };
+
     // =============================================================================================================
     // sweep 1: backward (ref: HMM.cpp:882-1041).  Step j = 0 .. len-2 handles p = len-2-j with the row of p+1.
     // =============================================================================================================
@@ -189,126 +678,34 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
       for (int j = 0; j < DEPTH && j < steps; ++j) {
         prefetchCoef(j);
       }
-      // beta at the last site: all ones (any positive scale is equivalent)
-      {
-        float4* out = betaSlot(0);
 #pragma unroll
-        for (int q = 0; q < SQ; ++q) {
-          out[q * 32 + lane] = make_float4(1.f, 1.f, 1.f, 1.f);
-        }
-#pragma unroll
-        for (int k = 0; k < S; ++k) {
-          a[k] = 1.f;
-        }
-        fenceProxyAsync();
-        __syncwarp();
-        if (lane == 0) {
-          bulkStore(slab + static_cast<size_t>(len - 1) * kBetaFloats, out, kBetaBytes);
-          bulkCommit();
-        }
+      for (int k = 0; k < S; ++k) {
+        a[k] = 1.f;  // beta at the last site: all ones (any positive scale is equivalent)
       }
-      for (int j = 0; j < steps; ++j) {
+      storeRow(a, len - 1, 0);
+      auto step = [&](const int j, float (&x)[S], float (&y)[S]) {
         const int p = len - 2 - j;
         const int slot = j % DEPTH;
         const int cls = bits.cls(from + p + 1);
         mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
         coefParity ^= 1u << slot;
-        const float* row = coefSlot(slot);
-        const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
-        const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
-        const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
-        const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
-        const float4* Rr = reinterpret_cast<const float4*>(row + 6 * Spad);
-        // vec = beta(p+1) * emission(p+1), in place in a
-#pragma unroll
-        for (int q = 0; q < SQ; ++q) {
-          const float4 e4 = E[q];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = 4 * q + i;
-            if (k < S) {
-              a[k] *= f4(e4, i);
-            }
-          }
-        }
-        // BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
-        {
-          float bu = 0.f;
-#pragma unroll
-          for (int q = SQ - 1; q >= 0; --q) {
-            const float4 u4 = Ur[q];
-            const float4 r4 = Rr[q];
-#pragma unroll
-            for (int i = 3; i >= 0; --i) {
-              const int k = 4 * q + i;
-              if (k == S - 1) {
-                c[k] = 0.f;
-              } else if (k < S - 1) {
-                bu = fmaf(f4(r4, i), bu, f4(u4, i) * a[k + 1]);
-                c[k] = bu;
-              }
-            }
-          }
-        }
-        // beta(p)[k] = BL + D[k] vec[k] + BU[k], BL += B[k-1] vec[k-1]; written over vec in a
-        {
-          float bl = 0.f, bPrev = 0.f, vPrev = 0.f;
-#pragma unroll
-          for (int q = 0; q < SQ; ++q) {
-            const float4 d4 = Dr[q];
-            const float4 b4 = Br[q];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = 4 * q + i;
-              if (k < S) {
-                const float v = a[k];
-                if (k) {
-                  bl = fmaf(bPrev, vPrev, bl);
-                }
-                a[k] = fmaf(f4(d4, i), v, bl) + c[k];
-                bPrev = f4(b4, i);
-                vPrev = v;
-              }
-            }
-          }
-        }
+        backwardStep<S>(x, y, coefSlot(slot), cls);
         __syncwarp();  // every lane is done with the coefficient slot
         if (j + DEPTH < steps) {
           prefetchCoef(j + DEPTH);
         }
         if ((p & (RESCALE - 1)) == 0) {
-          float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
-#pragma unroll
-          for (int k = 0; k < S; k += 4) {
-            s0 += a[k];
-            if (k + 1 < S) s1 += a[k + 1];
-            if (k + 2 < S) s2 += a[k + 2];
-            if (k + 3 < S) s3 += a[k + 3];
-          }
-          const float sc = 1.0f / ((s0 + s1) + (s2 + s3));
-#pragma unroll
-          for (int k = 0; k < S; ++k) {
-            a[k] *= sc;
-          }
+          scaleStates<S>(y, 1.0f / sumStates<S>(y));
         }
-        // stage the row and hand it to the copy engine
-        const int bslot = (j + 1) % DEPTH;
-        if (lane == 0) {
-          bulkWaitRead<DEPTH - 1>();  // the copy that last read this staging slot has drained it
-        }
-        __syncwarp();
-        float4* out = betaSlot(bslot);
-#pragma unroll
-        for (int q = 0; q < SQ; ++q) {
-          out[q * 32 + lane] = make_float4(a[4 * q], 4 * q + 1 < S ? a[4 * q + 1] : 0.f, 4 * q + 2 < S ? a[4 * q + 2] : 0.f,
-                                           4 * q + 3 < S ? a[4 * q + 3] : 0.f);
-        }
-        fenceProxyAsync();
-        __syncwarp();
-        if (lane == 0) {
-          bulkStore(slab + static_cast<size_t>(p) * kBetaFloats, out, kBetaBytes);
-          bulkCommit();
-        }
+        storeRow(y, p, (j + 1) % DEPTH);
+      };
+      int j = 0;
+      for (; j + 1 < steps; j += 2) {
+        step(j, a, c);
+        step(j + 1, c, a);
+      }
+      if (j < steps) {
+        step(j, a, c);
       }
       if (lane == 0) {
         bulkWaitAll<0>();  // all beta rows are in global memory before the forward sweep reads them back
@@ -334,76 +731,11 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
         prefetch(p);
       }
       CallerState cs;
-      for (int p = 0; p < len; ++p) {
+
+      // consumers of window position p: v = alpha(p); w = the other (dead) vector, receives q[k] = alpha[k] beta[k]
+      auto consume = [&](const int p, const float (&v)[S], float (&w)[S]) {
         const int site = from + p;
         const int slot = p % DEPTH;
-        const int cls = bits.cls(site);
-        mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
-        coefParity ^= 1u << slot;
-        const float* row = coefSlot(slot);
-        const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
-        if (p == 0) {
-#pragma unroll
-          for (int q = 0; q < SQ; ++q) {
-            const float4 e4 = E[q];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = 4 * q + i;
-              if (k < S) {
-                a[k] = fm.prior[k] * f4(e4, i);
-              }
-            }
-          }
-        } else {
-          const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
-          const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
-          const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
-          // alphaC[k] = sum_{j>=k} alpha(p-1)[j]; its head is the normaliser of alpha(p-1), for free
-          {
-            float run = 0.f;
-#pragma unroll
-            for (int k = S - 1; k >= 0; --k) {
-              run = (k == S - 1) ? a[k] : run + a[k];
-              c[k] = run;
-            }
-          }
-          const bool rescale = (p & (RESCALE - 1)) == 0;
-          const float sc = rescale ? 1.0f / c[0] : 1.0f;
-          float au = 0.f, uPrev = 0.f, crPrev = 0.f, aPrev = 0.f;
-#pragma unroll
-          for (int q = 0; q < SQ; ++q) {
-            const float4 e4 = E[q];
-            const float4 d4 = Dr[q];
-            const float4 b4 = Br[q];
-            const float4 u4 = Ur[q];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = 4 * q + i;
-              if (k < S) {
-                const float ak = a[k];
-                if (k) {
-                  au = fmaf(crPrev, au, uPrev * aPrev);
-                }
-                float term = fmaf(f4(d4, i), ak, au);
-                if (k < S - 1) {
-                  term = fmaf(f4(b4, i), c[k + 1], term);
-                }
-                a[k] = f4(e4, i) * term;
-                uPrev = f4(u4, i);
-                crPrev = fm.colRatios[k];
-                aPrev = ak;
-              }
-            }
-          }
-          if (rescale) {
-#pragma unroll
-            for (int k = 0; k < S; ++k) {
-              a[k] *= sc;
-            }
-          }
-        }
-
-        // ---- combine: q[k] = alpha[k] beta[k] (ref: HMM.cpp:672-680); the products stay in c for the consumers
         mbarWait(&bars[slot], (betaParity >> slot) & 1u);
         betaParity ^= 1u << slot;
         const float4* B4 = betaSlot(slot);
@@ -415,25 +747,24 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
           for (int i = 0; i < 4; ++i) {
             const int k = 4 * q + i;
             if (k < S) {
-              c[k] = a[k] * f4(b4, i);
+              w[k] = v[k] * f4(b4, i);
             }
           }
-          q0 += c[4 * q];
-          if (4 * q + 1 < S) q1 += c[4 * q + 1];
-          if (4 * q + 2 < S) q2 += c[4 * q + 2];
-          if (4 * q + 3 < S) q3 += c[4 * q + 3];
+          q0 += w[4 * q];
+          if (4 * q + 1 < S) q1 += w[4 * q + 1];
+          if (4 * q + 2 < S) q2 += w[4 * q + 2];
+          if (4 * q + 3 < S) q3 += w[4 * q + 3];
         }
-        const float r = 1.0f / ((q0 + q1) + (q2 + q3));
+        const float r = 1.0f / ((q0 + q1) + (q2 + q3));  // ref HMM.cpp:681-685
 
         if (wantSite) {
           float mean = 0.f, best = 0.f;
           int arg = 0;
 #pragma unroll
           for (int k = 0; k < S; ++k) {
-            const float post = c[k];
-            mean = fmaf(post, fm.expTimes[k], mean);
-            if (best < post) {
-              best = post;
+            mean = fmaf(w[k], fm.expTimes[k], mean);
+            if (best < w[k]) {
+              best = w[k];
               arg = k;
             }
           }
@@ -449,7 +780,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
 
         const bool inScan = wantSeg && site >= scanFrom && site < scanTo;
         if ((flags & FSMC_SITE_IBD) || inScan) {
-          forStatesBelow<S_T>(sT, [&](const int k) { ibdRaw += c[k]; });
+          forStatesBelow<S_T>(sT, [&](const int k) { ibdRaw += w[k]; });
           const float ibd = ibdRaw * r;
           if ((flags & FSMC_SITE_IBD) && laneActive) {
             args.siteIbd[static_cast<size_t>(pair) * args.siteStride + p] = ibd;
@@ -471,56 +802,48 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
             const bool changed = now != cs.level;
             const bool ending = changed && cs.level >= 0;  // the run that ended at site-1 is written now
             const bool closing = now >= 0 && site == scanTo - 1;
-            if constexpr (ACC) {
+            float* park = reinterpret_cast<float*>(betaSlot(slot)) + lane;  // this site's drained beta slot: [k][32]
+            if (__any_sync(kFull, ending)) {
               if (wantAge) {
-                if (__any_sync(kFull, ending)) {
-                  // rare: park the per-state sums (through site-1) in this site's drained beta slot for emitSegment
-                  float* park = reinterpret_cast<float*>(betaSlot(slot)) + lane;
+                // rare: park the per-state sums (through site-1) for emitSegment
 #pragma unroll
-                  for (int k = 0; k < S; ++k) {
-                    park[k * 32] = acc[k];
-                  }
-                  __syncwarp();
-                  if (ending) {
-                    emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, park, true);
-                  }
-                  __syncwarp();
+                for (int k = 0; k < (ACC ? S : 1); ++k) {
+                  park[k * 32] = acc[k];
                 }
-                if (__any_sync(kFull, now >= 0)) {
-                  // per-state sums of the current run: restart on a new run, accumulate otherwise
-                  // (ref: HMM.cpp:1209-1218,1229,1257,1284,1311)
-                  const float rr = now >= 0 ? r : 0.f;
-                  const float keep = changed ? 0.f : 1.f;
-                  forStatesBelow<S_T>(nAcc, [&](const int k) { acc[k] = fmaf(c[k], rr, keep * acc[k]); });
-                }
-                if (__any_sync(kFull, closing)) {
-                  float* park = reinterpret_cast<float*>(betaSlot(slot)) + lane;
-#pragma unroll
-                  for (int k = 0; k < S; ++k) {
-                    park[k * 32] = acc[k];
-                  }
-                  __syncwarp();
-                  if (closing) {
-                    emitSegment<false>(m, args, pair, cs.start, site, changed ? ibd : cs.prob + ibd, now, park, true);
-                  }
-                  __syncwarp();
-                }
+                __syncwarp();
+              }
+              if (ending) {
+                emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, park, wantAge);
+              }
+              __syncwarp();
+            }
+            if constexpr (ACC) {
+              if (wantAge && __any_sync(kFull, now >= 0)) {
+                // per-state sums of the current run: restart on a new run, accumulate otherwise
+                // (ref: HMM.cpp:1209-1218,1229,1257,1284,1311)
+                const float rr = now >= 0 ? r : 0.f;
+                const float keep = changed ? 0.f : 1.f;
+                forStatesBelow<S_T>(nAcc, [&](const int k) { acc[k] = fmaf(w[k], rr, keep * acc[k]); });
               }
             }
-            if (!wantAge) {
-              if (ending) {
-                emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, nullptr, false);
+            if (__any_sync(kFull, closing)) {
+              if (wantAge) {
+#pragma unroll
+                for (int k = 0; k < (ACC ? S : 1); ++k) {
+                  park[k * 32] = acc[k];
+                }
+                __syncwarp();
               }
               if (closing) {
-                emitSegment<false>(m, args, pair, cs.start, site, changed ? ibd : cs.prob + ibd, now, nullptr, false);
+                emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, park,
+                                   wantAge);
               }
+              __syncwarp();
             }
             if (now >= 0) {
+              cs.prob = changed ? ibd : cs.prob + ibd;
               if (changed) {
                 cs.start = site;
-                cs.prob = ibd;
-              } else {
-                cs.prob += ibd;
               }
               if (closing) {
                 cs.prob = 0.f;
@@ -535,6 +858,45 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
         if (p + DEPTH < len) {
           prefetch(p + DEPTH);
         }
+      };
+
+      // p = 0: alpha(from)[k] = prior[k] * emission  (ref HMM.cpp:736-743)
+      {
+        const int cls = bits.cls(from);
+        mbarWait(&bars[DEPTH], coefParity & 1u);
+        coefParity ^= 1u;
+        const float4* E = reinterpret_cast<const float4*>(coefSlot(0) + cls * Spad);
+#pragma unroll
+        for (int q = 0; q < SQ; ++q) {
+          const float4 e4 = E[q];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            const int k = 4 * q + i;
+            if (k < S) {
+              a[k] = fm.prior[k] * f4(e4, i);
+            }
+          }
+        }
+        consume(0, a, c);
+      }
+      auto step = [&](const int p, float (&x)[S], float (&y)[S]) {
+        const int slot = p % DEPTH;
+        const int cls = bits.cls(from + p);
+        mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
+        coefParity ^= 1u << slot;
+        const float total = forwardStep<S>(fm.colRatios, x, y, coefSlot(slot), cls);
+        if ((p & (RESCALE - 1)) == 0) {
+          scaleStates<S>(y, 1.0f / total);
+        }
+        consume(p, y, x);
+      };
+      int p = 1;
+      for (; p + 1 < len; p += 2) {
+        step(p, a, c);
+        step(p + 1, c, a);
+      }
+      if (p < len) {
+        step(p, a, c);
       }
     }
     __syncwarp();

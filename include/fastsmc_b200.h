@@ -107,6 +107,7 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, int64_t numHaps, in
 #define FSMC_EXACT 0x20u          /* unfused mul/add in the reference's NO_SSE operation order:   */
                                   /* results are bit-identical to the reference's NO_SSE build    */
 #define FSMC_GENERIC_KERNEL 0x40u /* force the any-S shared-memory kernel (testing)               */
+#define FSMC_WIDE_KERNEL 0x80u    /* never use the narrow (no beta round trip) kernel (testing)   */
 
 typedef struct fsmc_segment {
   uint32_t pair;     /* tile * 32 + lane                                                        */
@@ -148,6 +149,8 @@ typedef struct fsmc_decode_stats {
   int32_t kernelLaunches;
   int32_t statesKernel; /* S the kernel was specialised for, 0 = generic                          */
   int64_t scratchBytes; /* backward-sweep scratch in HBM                                          */
+  int32_t narrowKernel; /* 1 if the kernel without the beta round trip ran (states < threshold only) */
+  int32_t reserved;
 } fsmc_decode_stats;
 
 int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats* stats);

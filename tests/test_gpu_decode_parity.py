@@ -220,3 +220,38 @@ def test_fast_kernel_segments_69_states(synthetic69):
     np.testing.assert_allclose(g[:, 0], w[:, 0], rtol=REL_TOL)
     np.testing.assert_allclose(g[:, 1], w[:, 1], rtol=REL_TOL)
     assert (g[:, 2] != w[:, 2]).mean() < 5e-3
+
+
+def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69):
+    """FastSMC's default flags (age estimates conditional on TMRCA < time): the kernel that keeps only the states below
+    the threshold and carries the normaliser by the scale-factor recurrence (decodeNarrowKernel) gives the oracle's
+    segments and per-site IBD probabilities within 1e-4, over a 3 000-site window (750 rescalings)."""
+    from conftest import DQ_69
+    from fastsmc_b200 import _native as N
+    o_wide, ctx_wide = synthetic69
+    # a second oracle instance with conditional age estimates (ageThreshold == stateThreshold)
+    import glob
+    root = glob.glob("/tmp/pytest-of-*/pytest-*/syn69*/syn.hap.gz")[-1][:-len(".hap.gz")]
+    o = oracle_mod.Oracle(root, DQ_69, "/tmp/fsmc_test69n", hashing=False, time=50, noConditionalAgeEstimates=False,
+                          doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
+    ctx = context_from_oracle(o, oracle_mod)
+    assert o.age_threshold == o.state_threshold
+    rng = np.random.default_rng(11)
+    a, b = _pairs(rng, 96, o.num_haps)
+    # per-site IBD probability
+    mean, mp, ibd = o.decode_summary(a, b, 0, o.sites, mean=False, map_=False)
+    tiles = ctx.make_tiles(a, b, windows=[[0, o.sites]] * 3, sites=o.sites)
+    r = ctx.decode(tiles, N.SITE_IBD)
+    assert r.stats.narrowKernel == 1
+    np.testing.assert_allclose(r.site_ibd[tiles["rows"]], ibd, rtol=REL_TOL, atol=1e-12)
+    # segments with conditional age estimates: narrow vs the full-beta kernel (same arithmetic otherwise)
+    rn = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE)
+    rw = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE | N.WIDE_KERNEL)
+    assert rn.stats.narrowKernel == 1 and rw.stats.narrowKernel == 0
+    key = lambda s: (int(s["pair"]), int(s["posStart"]), int(s["posEnd"]))
+    gn, gw = {key(s): s for s in rn.segments}, {key(s): s for s in rw.segments}
+    common = sorted(set(gn) & set(gw))
+    assert len(common) >= 0.95 * max(len(gn), len(gw)) > 10
+    for f in ("prob", "postMean"):
+        np.testing.assert_allclose([gn[k][f] for k in common], [gw[k][f] for k in common], rtol=REL_TOL)
+    assert np.mean([gn[k]["mapState"] != gw[k]["mapState"] for k in common]) < 5e-3

@@ -24,7 +24,8 @@ if not os.path.exists(root + ".hap.gz"):
     synth.dataset(root, n_haps, n_sites, 3000 * n_sites, 1, 20201119)
 print("synth", time.time() - t)
 t = time.time()
-o = pyoracle.Oracle(root, dq, "/tmp/fsmc_probe/out", hashing=False, time=50, noConditionalAgeEstimates=True,
+cond = os.environ.get("PROBE_CONDITIONAL", "0") == "1"  # FastSMC's default: age estimates conditional on TMRCA < time
+o = pyoracle.Oracle(root, dq, "/tmp/fsmc_probe/out", hashing=False, time=50, noConditionalAgeEstimates=not cond,
                     doPerPairMAP=True, doPerPairPosteriorMean=True)
 print("oracle load", time.time() - t, o.sites, o.states, o.num_haps)
 ctx = context_from_oracle(o, pyoracle)
@@ -52,5 +53,5 @@ for flags, name in ((N.CALL_SEGMENTS | N.SEG_AGE, "segments+age"), (N.CALL_SEGME
         ps = r.stats.pairSites
         print(f"{name}: kernel {r.stats.kernelMs:.2f} ms  {ps / r.stats.kernelMs / 1e6:.3f} G pair-sites/s  "
               f"segs {r.stats.numSegments} scratch {r.stats.scratchBytes / 2**30:.1f} GiB  S_kernel {r.stats.statesKernel} "
-              f"beta GB/s {ps * o.states * 8 / r.stats.kernelMs / 1e6:.0f}")
+              f"beta GB/s {ps * o.states * 8 / r.stats.kernelMs / 1e6:.0f} narrow {r.stats.narrowKernel}")
     plan.close()
