@@ -163,6 +163,17 @@ def cpu_baseline(seconds_budget=15.0):
             "sample": f"first {n_pairs} pairs of the job x {N_SITES} sites, {cores} threads, {dt:.1f} s"}
 
 
+def max_over_ranks(value, world, device="cuda"):
+    """Step time of the job = the slowest rank's (the only cross-rank operation of the benchmark)."""
+    if world == 1:
+        return float(value)
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([value], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    return float(t.item())
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -243,12 +254,34 @@ def main():
     scratch_bytes = int(r.stats.scratchBytes)
     launches_per_step = int(r.stats.kernelLaunches)
     plan.close()
-    t = torch.tensor([total_ms], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    total_ms = float(t.item())
+    total_ms = max_over_ranks(total_ms, world)
     ms_per_step = total_ms / args.steps
     value = world * pair_sites / (ms_per_step / 1e3)
+
+    # ---- the same job with FastSMC's command-line default age estimates (conditional on TMRCA < time, i.e.
+    # noConditionalAgeEstimates off: only the states below the threshold are consumed -> decodeNarrowKernel) ------------
+    ctx2 = N.Context(local)
+    ctx2.set_stream(stream.cuda_stream)
+    ctx2.set_model(**dict(tables, age_threshold=tables["state_threshold"]))
+    ctx2.set_haplotypes(data.hapBits, L)
+    plan2 = ctx2.plan(tiles, flags, segment_capacity=1 << 21)
+    for _ in range(args.warmup):
+        plan2.launch()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(args.steps):
+        plan2.launch()
+    e1.record(stream)
+    barrier()
+    narrow_ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    r2 = plan2.collect()
+    narrow = {"value": world * pair_sites / (narrow_ms / 1e3), "unit": "pair-sites/s", "ms_per_step": narrow_ms,
+              "kernel": "decodeNarrowKernel<69>" if r2.stats.narrowKernel else "decodeFastKernel<69>",
+              "segments_per_step": int(r2.stats.numSegments), "scratch_bytes": int(r2.stats.scratchBytes),
+              "flags": "as the headline run but age estimates conditional on TMRCA < time (FastSMC_exe default)"}
+    plan2.close()
+    ctx2.close()
 
     # ---- e2e: fsmc_decode with host buffers -----------------------------------------------------------------------------
     for _ in range(2):
@@ -259,10 +292,7 @@ def main():
         res = ctx.decode(tiles, flags, segment_capacity=1 << 21)
     torch.cuda.synchronize()
     e2e_s = (time.perf_counter() - t0) / args.steps
-    t = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_s = float(t.item())
+    e2e_s = max_over_ranks(e2e_s, world)
     h2d = sum(tiles[k].nbytes for k in ("hapA", "hapB", "tilePairs", "tileFrom", "tileTo", "tileScanFrom", "tileScanTo"))
     d2h = int(res.stats.numSegments) * N.SEGMENT_DTYPE.itemsize + 16
     e2e = {"value": world * pair_sites / e2e_s, "unit": "pair-sites/s", "h2d_bytes_per_step": int(h2d),
@@ -302,6 +332,8 @@ def main():
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD, "pairs_per_gpu": int(len(a)), "sites": int(L), "states": int(S),
                        "pair_sites_per_step_per_gpu": pair_sites, "segments_per_step": n_segments,
+                       "flags": "segment length + per-segment posterior mean + MAP over ALL states (noConditionalAgeEstimates), "
+                                "the reference's regression-test / FastSMC-constructor defaults",
                        "l2": f"no flush needed: each step streams {scratch_bytes / 2**30:.0f} GiB of backward-sweep scratch "
                              "through HBM (>> 126 MB L2)", "parallelism": f"{world} independent jobs, one per GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
@@ -311,6 +343,10 @@ def main():
             "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
                               "flops_per_pair_site": FLOPS_PER_PAIR_SITE_STATE * S,
                               "peak_source": "SMs x 128 lanes x 2 x 1.965 GHz (nominal)"},
+            "default_flags": dict(narrow, roofline={"bound": "fp32", "achieved": narrow["value"] / world * FLOPS_PER_PAIR_SITE_STATE * S / 1e12,
+                                                     "peak": fp32_peak, "unit": "TFLOP/s",
+                                                     "frac": narrow["value"] / world * FLOPS_PER_PAIR_SITE_STATE * S / 1e12 / fp32_peak,
+                                                     "traffic": None}),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
             "ibd_wall": ibd_wall,
         }

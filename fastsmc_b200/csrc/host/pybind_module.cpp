@@ -14,6 +14,7 @@
 #include "FastSMC.hpp"
 #include "HMM.hpp"
 #include "HmmUtils.hpp"
+#include "Partitioner.hpp"
 
 namespace py = pybind11;
 using namespace py::literals;
@@ -357,6 +358,22 @@ PYBIND11_MODULE(pyASMC, m)
       .def("get_ref_of_results", &ASMC::ASMC::getRefOfResults, py::return_value_policy::reference_internal)
       .def("hmm", &ASMC::ASMC::hmm, py::return_value_policy::reference_internal);
 
+
+  // multi-GPU: the jobs of one data set dealt to the GPUs of the box (no collective; ref: FastSMC_example_multiple_jobs.sh)
+  py::class_<ASMC::JobReport>(m, "JobReport")
+      .def_readonly("jobInd", &ASMC::JobReport::jobInd)
+      .def_readonly("device", &ASMC::JobReport::device)
+      .def_readonly("candidates", &ASMC::JobReport::candidates)
+      .def_readonly("pairsDecoded", &ASMC::JobReport::pairsDecoded)
+      .def_readonly("segments", &ASMC::JobReport::segments)
+      .def_readonly("pairSites", &ASMC::JobReport::pairSites)
+      .def_readonly("kernelMs", &ASMC::JobReport::kernelMs)
+      .def_readonly("seedMs", &ASMC::JobReport::seedMs)
+      .def_readonly("wallSeconds", &ASMC::JobReport::wallSeconds)
+      .def_readonly("error", &ASMC::JobReport::error);
+  m.def("jobOrder", &ASMC::jobOrder, "jobs"_a);
+  m.def("jobsOfRank", &ASMC::jobsOfRank, "jobs"_a, "world"_a, "rank"_a);
+  m.def("runAllJobs", &ASMC::runAllJobs, "params"_a, "devices"_a, py::call_guard<py::gil_scoped_release>());
 
   // host-only pieces, callable without a GPU (used by the CPU test-suite)
   m.def(

@@ -143,3 +143,24 @@ def test_asmc_decode_pairs_per_site_outputs(asmc, oracle_mod):
             assert (got_map != mp).mean() < 1e-3
         assert np.array_equal(np.array(res.min_posterior_means), got_mean.min(axis=0))
         assert np.array_equal(np.array(res.argmin_posterior_means), got_mean.argmin(axis=0))
+
+
+def test_all_jobs_partitioned_over_host_threads(asmc, oracle_mod, tmp_path):
+    """The jobs/jobInd partition (ref: Data.cpp:62-80, FastSMC_example_multiple_jobs.sh): J=4 jobs of the example data
+    dealt to two host threads (two contexts; on a multi-GPU box: two GPUs).  Every job's file equals the oracle's for that
+    jobInd, and the union of the jobs' pairs is the single-job run's."""
+    p = _params(asmc, str(tmp_path / "gpu"), exactArithmetic=True, jobs=4)
+    reports = asmc.pyASMC.runAllJobs(p, [0, 0])
+    assert [r.jobInd for r in reports] == [1, 2, 3, 4] and all(r.error == "" for r in reports)
+    total = 0
+    for r in reports:
+        got = _lines(f"{p.outFileRoot}.{r.jobInd}.4.FastSMC.ibd.gz")
+        o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, jobs=4,
+                              jobInd=r.jobInd, **REGRESSION_PARAMS)
+        ref_path = str(tmp_path / f"oracle{r.jobInd}.ibd.gz")
+        n = o.run(ref_path)
+        assert got == _lines(ref_path) and len(got) == n == r.segments
+        assert r.candidates == len(o.candidates())
+        total += r.candidates
+    one = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o1"), hashing=True, **REGRESSION_PARAMS)
+    assert total == len(one.seed())  # the four triangles tile the pair matrix exactly
