@@ -1,12 +1,14 @@
 // fastsmc_b200 — implementation of the C ABI declared in include/fastsmc_b200.h.
 // Host side of the decode path: device buffers, model assembly, tile scheduling, launches.
 #include <algorithm>
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "decode_kernels.cuh"
@@ -64,7 +66,38 @@ template <class T> struct DevBuf {
   }
 };
 
+// Page-locked host staging buffer (grow-only): device-to-host copies of the segment records run at full PCIe rate
+// and without the driver's pageable bounce copy.
+template <class T> struct PinnedBuf {
+  T* p = nullptr;
+  size_t n = 0;
+  ~PinnedBuf() { release(); }
+  void release()
+  {
+    if (p) {
+      cudaFreeHost(p);
+      p = nullptr;
+      n = 0;
+    }
+  }
+  cudaError_t ensure(const size_t count)
+  {
+    if (count <= n && p) {
+      return cudaSuccess;
+    }
+    release();
+    const size_t want = std::max<size_t>(count + count / 4, 1);
+    const cudaError_t e = cudaHostAlloc(reinterpret_cast<void**>(&p), want * sizeof(T), cudaHostAllocDefault);
+    if (e == cudaSuccess) {
+      n = want;
+    }
+    return e;
+  }
+};
+
 }  // namespace
+
+struct fsmc_plan;
 
 struct fsmc_ctx {
   int device = 0;
@@ -87,6 +120,12 @@ struct fsmc_ctx {
   DevBuf<float> seedGenPos;
   DevBuf<fsmc_match> seedOut;
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+  // host staging of segment records and the per-pair counters of their counting sort (fsmc_plan_collect)
+  PinnedBuf<fsmc_segment> segStage;
+  std::vector<uint32_t> pairOffset;
+  // a destroyed plan is parked here so that the next fsmc_plan_create reuses its device buffers (fsmc_decode makes
+  // one plan per call; cudaMalloc/cudaFree per call would serialise the device)
+  fsmc_plan* sparePlan = nullptr;
 };
 
 struct fsmc_plan {
@@ -98,6 +137,7 @@ struct fsmc_plan {
   long long siteStride = 0;
   DevBuf<uint32_t> hapA, hapB;
   DevBuf<int> tilePairs, tileFrom, tileTo, scanFrom, scanTo, order;
+  std::vector<int> hostOrder;  // source of the asynchronous copy into `order`
   DevBuf<fsmc_segment> segments;
   DevBuf<unsigned long long> counters;  // [0] segment count, [1] tile queue head
   DevBuf<float> siteMean, siteIbd;
@@ -275,6 +315,7 @@ int fsmc_ctx_destroy(fsmc_ctx* ctx)
   if (ctx->ownStream) {
     cudaStreamDestroy(ctx->ownStream);
   }
+  delete ctx->sparePlan;
   delete ctx;
   return FSMC_OK;
 }
@@ -446,7 +487,8 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   }
 
   FSMC_CUDA(cudaSetDevice(ctx->device));
-  auto* plan = new fsmc_plan;
+  fsmc_plan* plan = ctx->sparePlan ? ctx->sparePlan : new fsmc_plan;
+  ctx->sparePlan = nullptr;
   struct Guard {
     fsmc_plan*& p;
     bool keep = false;
@@ -467,7 +509,8 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   plan->siteStride = siteOut ? req->siteStride : 0;
 
   // longest-window-first launch order (dynamic queue → LPT schedule); stable, so equal windows keep input order
-  std::vector<int> order(T);
+  std::vector<int>& order = plan->hostOrder;
+  order.resize(T);
   std::iota(order.begin(), order.end(), 0);
   std::stable_sort(order.begin(), order.end(), [&](const int x, const int y) {
     return (req->tileTo[x] - req->tileFrom[x]) > (req->tileTo[y] - req->tileFrom[y]);
@@ -509,7 +552,8 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   if (flags & FSMC_SITE_IBD) {
     FSMC_CUDA(plan->siteIbd.ensure(nSite));
   }
-  FSMC_CUDA(cudaStreamSynchronize(st));  // `order` is a local
+  plan->launched = false;
+  plan->launches = 0;
 
   // ---- launch geometry --------------------------------------------------------------------------
   const KernelChoice kc = chooseKernel(m.S, flags);
@@ -653,7 +697,8 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
       if (!out->segments || out->segmentCapacity < stored) {
         return fail(FSMC_E_INVALID, "fsmc_plan_collect: segment buffer missing or smaller than at plan creation");
       }
-      FSMC_CUDA(cudaMemcpyAsync(out->segments, plan->segments.p, stored * sizeof(fsmc_segment), cudaMemcpyDeviceToHost,
+      FSMC_CUDA(ctx->segStage.ensure(static_cast<size_t>(stored)));
+      FSMC_CUDA(cudaMemcpyAsync(ctx->segStage.p, plan->segments.p, stored * sizeof(fsmc_segment), cudaMemcpyDeviceToHost,
                                 st));
     }
   }
@@ -679,10 +724,30 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
   FSMC_CUDA(cudaEventRecord(ctx->ev[3], st));
   FSMC_CUDA(cudaStreamSynchronize(st));
   if (stored > 0) {
-    // reference order: batches in submission order, pairs in batch order, sites ascending
-    std::sort(out->segments, out->segments + stored, [](const fsmc_segment& x, const fsmc_segment& y) {
-      return x.pair != y.pair ? x.pair < y.pair : x.posStart < y.posStart;
-    });
+    // reference order: batches in submission order, pairs in batch order, sites ascending.  A lane appends its
+    // segments in ascending site order, so a stable counting sort by pair from the staging buffer into the caller's
+    // buffer restores it in O(n); the insertion pass is a guard that never moves anything in practice.
+    const fsmc_segment* in = ctx->segStage.p;
+    std::vector<uint32_t>& off = ctx->pairOffset;
+    const size_t nPairs = static_cast<size_t>(plan->numTiles) * 32;
+    off.assign(nPairs + 1, 0u);
+    for (long long i = 0; i < stored; ++i) {
+      if (in[i].pair >= nPairs) {
+        return fail(FSMC_E_CUDA, "fsmc_plan_collect: corrupt segment record (pair %u of %zu)", in[i].pair, nPairs);
+      }
+      ++off[in[i].pair + 1];
+    }
+    for (size_t q = 0; q < nPairs; ++q) {
+      off[q + 1] += off[q];
+    }
+    for (long long i = 0; i < stored; ++i) {
+      fsmc_segment* dst = out->segments + off[in[i].pair]++;
+      *dst = in[i];
+      while (dst > out->segments && dst[-1].pair == dst->pair && dst[-1].posStart > dst->posStart) {
+        std::swap(dst[-1], dst[0]);
+        --dst;
+      }
+    }
   }
   if (found > plan->segmentCapacity) {
     rc = fail(FSMC_E_OVERFLOW, "fsmc_plan_collect: %lld segments found, capacity %lld", found, plan->segmentCapacity);
@@ -711,6 +776,10 @@ int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan)
   if (ctx) {
     cudaSetDevice(ctx->device);
     cudaStreamSynchronize(ctx->stream);
+    if (plan && !ctx->sparePlan) {
+      ctx->sparePlan = plan;  // keeps its device buffers for the next plan
+      return FSMC_OK;
+    }
   }
   delete plan;
   return FSMC_OK;
@@ -818,15 +887,44 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   const long long found = static_cast<long long>(counters[3]);
   const long long stored = std::min<long long>(found, capacity);
   if (stored > 0) {
-    FSMC_CUDA(cudaMemcpyAsync(out, ctx->seedOut.p, stored * sizeof(fsmc_match), cudaMemcpyDeviceToHost, st));
+    // canonical candidate order (endWord, hapA, hapB): counting sort by end word from a staging copy into the
+    // caller's buffer, then every end-word bucket is sorted by pair on its own host thread
+    std::vector<fsmc_match> stage(static_cast<size_t>(stored));
+    FSMC_CUDA(cudaMemcpyAsync(stage.data(), ctx->seedOut.p, stored * sizeof(fsmc_match), cudaMemcpyDeviceToHost, st));
     FSMC_CUDA(cudaStreamSynchronize(st));
-    // canonical candidate order
-    std::sort(out, out + stored, [](const fsmc_match& x, const fsmc_match& y) {
-      if (x.endWord != y.endWord) {
-        return x.endWord < y.endWord;
+    std::vector<size_t> begin(static_cast<size_t>(W) + 2, 0);
+    for (const fsmc_match& mt : stage) {
+      if (mt.endWord < 0 || mt.endWord >= W) {
+        return fail(FSMC_E_CUDA, "fsmc_seed: corrupt match record (end word %d of %d)", mt.endWord, W);
       }
-      return x.hapA != y.hapA ? x.hapA < y.hapA : x.hapB < y.hapB;
-    });
+      ++begin[static_cast<size_t>(mt.endWord) + 1];
+    }
+    for (int w = 0; w < W; ++w) {
+      begin[w + 1] += begin[w];
+    }
+    {
+      std::vector<size_t> cursor(begin.begin(), begin.begin() + W);
+      for (const fsmc_match& mt : stage) {
+        out[cursor[mt.endWord]++] = mt;
+      }
+    }
+    std::atomic<int> nextBucket{0};
+    auto sortBuckets = [&] {
+      for (int w = nextBucket++; w < W; w = nextBucket++) {
+        std::sort(out + begin[w], out + begin[w + 1], [](const fsmc_match& x, const fsmc_match& y) {
+          return x.hapA != y.hapA ? x.hapA < y.hapA : x.hapB < y.hapB;
+        });
+      }
+    };
+    const unsigned nThreads = stored < (1 << 16) ? 1u : std::min(32u, std::max(1u, std::thread::hardware_concurrency()));
+    std::vector<std::thread> pool;
+    for (unsigned t = 1; t < nThreads; ++t) {
+      pool.emplace_back(sortBuckets);
+    }
+    sortBuckets();
+    for (auto& th : pool) {
+      th.join();
+    }
   }
   if (stats) {
     stats->numMatches = found;

@@ -2,6 +2,8 @@
 #include "Data.hpp"
 
 #include <algorithm>
+#include <thread>
+#include <atomic>
 #include <cmath>
 #include <cstdlib>
 #include <iostream>
@@ -434,12 +436,19 @@ Individual Data::individual(const unsigned long i) const
   return ind;
 }
 
-// ref: Data.cpp:144-160 (sampleHypergeometric) and 567-599.  The sequence of std::rand() calls and the
-// std::shuffle draws must match the reference's exactly, so this loop is deliberately serial.
+// ref: Data.cpp:144-160 (sampleHypergeometric) and 567-599.  The reference seeds one std::mt19937 per draw from
+// std::rand(); the sequence of std::rand() calls must match the reference's exactly, so the seeds are drawn serially,
+// in the reference's order.  The shuffles themselves only depend on their seed and run on all host threads (at UK
+// Biobank scale they are 3 x sites shuffles of ~10^6 shorts).
 std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int numCsfsSamples) const
 {
   std::vector<std::vector<int>> counts(sites, std::vector<int>(3, 0));
-  std::vector<unsigned short> urn;
+  struct Draw {
+    int site, dist, population, successes;
+    unsigned seed;
+  };
+  std::vector<Draw> draws;
+  draws.reserve(static_cast<size_t>(sites) * 3);
   for (int s = 0; s < sites; ++s) {
     const int total = totalSamplesCount[s];
     const int derived = derivedAlleleCounts[s];
@@ -451,13 +460,41 @@ std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int num
     for (int dist = 0; dist < 3; ++dist) {
       const int population = total - 2;
       const int successes = derived - dist;
-      int sample = -1;
       if (successes >= 0 && successes <= population) {
-        urn.assign(population, 0);
-        std::fill(urn.begin(), urn.begin() + successes, 1);
-        std::shuffle(urn.begin(), urn.end(), std::mt19937(std::rand()));
-        sample = std::accumulate(urn.begin(), urn.begin() + (numCsfsSamples - 2), 0);
+        draws.push_back(Draw{s, dist, population, successes, static_cast<unsigned>(std::rand())});
+      } else {
+        counts[s][dist] = -1;
       }
+    }
+  }
+  std::atomic<size_t> next{0};
+  auto work = [&] {
+    std::vector<unsigned short> urn;
+    constexpr size_t kGrain = 16;
+    for (size_t lo = next.fetch_add(kGrain); lo < draws.size(); lo = next.fetch_add(kGrain)) {
+      const size_t hi = std::min(draws.size(), lo + kGrain);
+      for (size_t i = lo; i < hi; ++i) {
+        const Draw& d = draws[i];
+        urn.assign(d.population, 0);
+        std::fill(urn.begin(), urn.begin() + d.successes, 1);
+        std::shuffle(urn.begin(), urn.end(), std::mt19937(d.seed));
+        counts[d.site][d.dist] = std::accumulate(urn.begin(), urn.begin() + (numCsfsSamples - 2), 0);
+      }
+    }
+  };
+  const size_t cost = draws.empty() ? 0 : draws.size() * static_cast<size_t>(std::max(1, draws[0].population));
+  const unsigned nThreads = cost < (size_t{1} << 24) ? 1u : std::max(1u, std::thread::hardware_concurrency());
+  std::vector<std::thread> pool;
+  for (unsigned t = 1; t < nThreads; ++t) {
+    pool.emplace_back(work);
+  }
+  work();
+  for (auto& th : pool) {
+    th.join();
+  }
+  for (int s = 0; s < sites; ++s) {
+    for (int dist = 0; dist < 3; ++dist) {
+      int sample = counts[s][dist];
       if (foldToMinorAlleles && (sample + dist > numCsfsSamples / 2)) {
         sample = numCsfsSamples - 2 - sample;
       }

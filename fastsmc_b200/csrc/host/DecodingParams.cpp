@@ -195,7 +195,8 @@ bool DecodingParams::processCommandLineArgsFastSMC(int argc, char* argv[])
   t.strings = {{"inFileRoot", &inFileRoot}, {"outFileRoot", &outFileRoot}, {"decodingQuantFile", &decodingQuantFile},
                {"mode", &modeShadow}};
   t.ints = {{"time", &time}, {"jobs", &jobs}, {"jobInd", &jobInd}, {"batchSize", &batchSize},
-            {"recall", &recallThreshold}, {"gap", &gap}, {"max_seeds", &max_seeds}, {"device", &device}};
+            {"recall", &recallThreshold}, {"gap", &gap}, {"max_seeds", &max_seeds}, {"device", &device},
+            {"outputCompressionLevel", &outputCompressionLevel}, {"outputThreads", &outputThreads}};
   t.floats = {{"skipCSFSdistance", &skipCSFSdistance}, {"min_m", &min_m}, {"skip", &skip}, {"min_maf", &min_maf}};
   t.switches = {{"bin", &BIN_OUT}, {"segmentLength", &outputIbdSegmentLength}, {"perPairMAP", &doPerPairMAP},
                 {"perPairPosteriorMeans", &doPerPairPosteriorMean},

@@ -66,6 +66,10 @@ public:
   // order (needed for record-for-record identical output).  false = canonical order
   // (flush word, then pair key), which is cheaper at scale.
   bool referenceCandidateOrder = true;
+  // B200 build only: the IBD file is written as concatenated gzip members compressed on `outputThreads` host
+  // threads (0 = all cores) at this zlib level; gunzip yields the reference's byte stream at any level.
+  int outputCompressionLevel = 1;
+  int outputThreads = 0;
 
   bool processOptions();
   bool processCommandLineArgs(int argc, char* argv[]);

@@ -11,9 +11,12 @@
 #include <map>
 #include <stdexcept>
 
+#include <charconv>
+#include <memory>
+
 #include "../../../include/fastsmc_b200.h"
-#include "GzWriter.hpp"
 #include "HmmUtils.hpp"
+#include "OutputPipeline.hpp"
 
 namespace
 {
@@ -30,20 +33,38 @@ void check(const int rc, const char* what)
   }
 }
 
-// printf("%.7g") is what the reference's ostream produces for floats at precision 7 (ref: HMM.cpp:1116-1141)
+// printf("%.7g") is what the reference's ostream produces for floats at precision 7 (ref: HMM.cpp:1116-1141);
+// std::to_chars with chars_format::general and a precision is specified to give the same characters, several times
+// faster.
 void appendG7(std::string& s, const double v)
 {
   char buf[48];
-  const int n = std::snprintf(buf, sizeof buf, "\t%.7g", v);
-  s.append(buf, n);
+  buf[0] = '\t';
+  const auto r = std::to_chars(buf + 1, buf + sizeof buf, v, std::chars_format::general, 7);
+  s.append(buf, static_cast<size_t>(r.ptr - buf));
+}
+
+void appendInt(std::string& s, const long v)
+{
+  char buf[24];
+  const auto r = std::to_chars(buf, buf + sizeof buf, v);
+  s.append(buf, static_cast<size_t>(r.ptr - buf));
 }
 
 }  // namespace
 
 struct HMM::GzOut {
-  GzWriter writer;
-  std::string line;
-  explicit GzOut(const std::string& path) : writer(path) {}
+  OutputPipeline writer;
+  std::vector<std::string> idPrefix;  // "fam\tiid\t" per individual (text output)
+  explicit GzOut(const std::string& path, const int level, const unsigned threads) : writer(path, level, threads) {}
+};
+
+// The segments of one decoded chunk, shared by the formatting tasks of the output pipeline.
+struct HMM::SegmentBlock {
+  std::vector<Pending> pend;         // the chunk's pairs
+  std::vector<uint32_t> firstPair;   // tile -> index of its lane 0 in pend
+  std::unique_ptr<fsmc_segment[]> seg;
+  size_t count = 0;
 };
 
 HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/)
@@ -250,7 +271,14 @@ void HMM::openOutput(const int jobs, const int jobInd)
 {
   const std::string path = decodingParams.outFileRoot + "." + std::to_string(jobInd) + "." + std::to_string(jobs) +
                            (decodingParams.BIN_OUT ? ".FastSMC.bibd.gz" : ".FastSMC.ibd.gz");
-  m_out = std::make_unique<GzOut>(path);
+  m_out = std::make_unique<GzOut>(path, decodingParams.outputCompressionLevel,
+                                  static_cast<unsigned>(std::max(0, decodingParams.outputThreads)));
+  if (!decodingParams.BIN_OUT) {
+    m_out->idPrefix.reserve(data.FamIDList.size());
+    for (size_t i = 0; i < data.FamIDList.size(); ++i) {
+      m_out->idPrefix.push_back(data.FamIDList[i] + '\t' + data.IIDList[i] + '\t');
+    }
+  }
   if (decodingParams.BIN_OUT) {
     auto& w = m_out->writer;
     w.write(&decodingParams.outputIbdSegmentLength, sizeof(bool));
@@ -484,7 +512,7 @@ TileSet buildTiles(const P* pend, const size_t n, const size_t batchSize, const 
 
 void HMM::runSegmentChunk(const Pending* pend, const size_t n)
 {
-  const TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), m_windowed, data.geneticPositions, data.sites);
+  TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), m_windowed, data.geneticPositions, data.sites);
   const bool ages = decodingParams.doPerPairPosteriorMean || decodingParams.doPerPairMAP;
   fsmc_decode_request req{};
   req.numTiles = static_cast<int64_t>(t.pairs.size());
@@ -496,21 +524,25 @@ void HMM::runSegmentChunk(const Pending* pend, const size_t n)
   req.tileScanFrom = t.scanFrom.data();
   req.tileScanTo = t.scanTo.data();
   req.flags = FSMC_CALL_SEGMENTS | (ages ? FSMC_SEG_AGE : 0u) | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
-  std::vector<fsmc_segment> seg(std::max<size_t>(1024, n * 2));
+  // record buffer sized from the densest chunk seen so far (a retry after FSMC_E_OVERFLOW decodes the chunk again)
+  size_t capacity = std::max<size_t>(1024, static_cast<size_t>(static_cast<double>(n) * m_segmentsPerPair * 1.5) + 1024);
+  auto block = std::make_shared<SegmentBlock>();
   fsmc_decode_stats st{};
   for (;;) {
-    req.segments = seg.data();
-    req.segmentCapacity = static_cast<int64_t>(seg.size());
+    block->seg.reset(new fsmc_segment[capacity]);
+    req.segments = block->seg.get();
+    req.segmentCapacity = static_cast<int64_t>(capacity);
     const double t0 = now();
     const int rc = fsmc_decode(m_ctx, &req, &st);
     m_stats.decodeWallS += now() - t0;
     if (rc == FSMC_E_OVERFLOW) {
-      seg.resize(static_cast<size_t>(st.numSegments) + 1024);
+      capacity = static_cast<size_t>(st.numSegments) + 1024;
       continue;
     }
     check(rc, "fsmc_decode");
     break;
   }
+  m_segmentsPerPair = std::max(m_segmentsPerPair, static_cast<double>(st.numSegments) / static_cast<double>(n));
   m_stats.decodeCalls += 1;
   m_stats.pairsDecoded += n;
   m_stats.batches += (n + m_batchSize - 1) / m_batchSize;
@@ -519,91 +551,103 @@ void HMM::runSegmentChunk(const Pending* pend, const size_t n)
   m_stats.deviceMs += st.totalMs;
 
   const double t1 = now();
-  for (int64_t i = 0; i < st.numSegments; ++i) {
-    const fsmc_segment& g = seg[i];
-    const size_t p = t.firstPair[g.pair / FSMC_TILE] + (g.pair % FSMC_TILE);
-    IbdSegment s;
-    // first haplotype of the pair is printed first (ref: HMM.cpp:483-486, 1116-1121)
-    s.ind1 = pend[p].hapA / 2;
-    s.hap1 = 1 + static_cast<int>(pend[p].hapA % 2);
-    s.ind2 = pend[p].hapB / 2;
-    s.hap2 = 1 + static_cast<int>(pend[p].hapB % 2);
-    s.posStart = g.posStart;
-    s.posEnd = g.posEnd;
-    s.prob = g.prob;
-    s.postMean = g.postMean;
-    s.mapTime = g.mapTime;
-    writeSegment(s);
+  const size_t count = static_cast<size_t>(st.numSegments);
+  nbSegmentsDetected += count;
+  m_stats.segments += count;
+  block->count = count;
+  block->pend.assign(pend, pend + n);
+  block->firstPair = std::move(t.firstPair);
+  if (m_keepSegments) {
+    m_segments.reserve(m_segments.size() + count);
+    for (size_t i = 0; i < count; ++i) {
+      m_segments.push_back(toIbdSegment(*block, i));
+    }
+  }
+  if (m_out && count > 0) {
+    // formatting + compression happen on the pipeline's threads, in blocks that become one gzip member each
+    constexpr size_t kRecordsPerTask = size_t{1} << 15;
+    for (size_t lo = 0; lo < count; lo += kRecordsPerTask) {
+      const size_t hi = std::min(count, lo + kRecordsPerTask);
+      m_out->writer.submit([this, block, lo, hi](std::string& out) { formatSegments(*block, lo, hi, out); });
+    }
   }
   m_stats.outputWallS += now() - t1;
 }
 
-// ref: HMM.cpp:1110-1177
-void HMM::writeSegment(const IbdSegment& s)
+IbdSegment HMM::toIbdSegment(const SegmentBlock& block, const size_t i) const
 {
-  ++nbSegmentsDetected;
-  ++m_stats.segments;
-  if (m_keepSegments) {
-    m_segments.push_back(s);
-  }
-  if (!m_out) {
-    return;
-  }
-  const int bpStart = data.physicalPositions[s.posStart], bpEnd = data.physicalPositions[s.posEnd];
-  const float cm = 100.f * (data.geneticPositions[s.posEnd] - data.geneticPositions[s.posStart]);
-  const double score = s.prob / static_cast<double>(static_cast<unsigned>(s.posEnd - s.posStart) + 1u);
-  auto& w = m_out->writer;
-  if (!decodingParams.BIN_OUT) {
-    std::string& l = m_out->line;
-    l.clear();
-    l += data.FamIDList[s.ind1];
-    l += '\t';
-    l += data.IIDList[s.ind1];
-    l += '\t';
-    l += std::to_string(s.hap1);
-    l += '\t';
-    l += data.FamIDList[s.ind2];
-    l += '\t';
-    l += data.IIDList[s.ind2];
-    l += '\t';
-    l += std::to_string(s.hap2);
-    l += '\t';
-    l += std::to_string(data.chrNumber);
-    l += '\t';
-    l += std::to_string(bpStart);
-    l += '\t';
-    l += std::to_string(bpEnd);
-    if (decodingParams.outputIbdSegmentLength) {
-      appendG7(l, static_cast<double>(cm));
-    }
-    appendG7(l, score);
-    if (decodingParams.doPerPairPosteriorMean) {
-      appendG7(l, static_cast<double>(s.postMean));
-    }
-    if (decodingParams.doPerPairMAP) {
-      appendG7(l, static_cast<double>(s.mapTime));
-    }
-    l += '\n';
-    w.write(l);
-  } else {
-    const unsigned ind[2] = {s.ind1, s.ind2};
-    const uint8_t hp[2] = {static_cast<uint8_t>(s.hap1), static_cast<uint8_t>(s.hap2)};
-    const float scoreF = static_cast<float>(score);
-    w.write(&ind[0], sizeof(unsigned));
-    w.write(&hp[0], 1);
-    w.write(&ind[1], sizeof(unsigned));
-    w.write(&hp[1], 1);
-    w.write(&bpStart, sizeof(int));
-    w.write(&bpEnd, sizeof(int));
-    if (decodingParams.outputIbdSegmentLength) {
-      w.write(&cm, sizeof(float));
-    }
-    w.write(&scoreF, sizeof(float));
-    if (decodingParams.doPerPairPosteriorMean) {
-      w.write(&s.postMean, sizeof(float));
-    }
-    if (decodingParams.doPerPairMAP) {
-      w.write(&s.mapTime, sizeof(float));
+  const fsmc_segment& g = block.seg[i];
+  const Pending& pr = block.pend[block.firstPair[g.pair / FSMC_TILE] + (g.pair % FSMC_TILE)];
+  IbdSegment s;
+  // first haplotype of the pair is printed first (ref: HMM.cpp:483-486, 1116-1121)
+  s.ind1 = pr.hapA / 2;
+  s.hap1 = 1 + static_cast<int>(pr.hapA % 2);
+  s.ind2 = pr.hapB / 2;
+  s.hap2 = 1 + static_cast<int>(pr.hapB % 2);
+  s.posStart = g.posStart;
+  s.posEnd = g.posEnd;
+  s.prob = g.prob;
+  s.postMean = g.postMean;
+  s.mapTime = g.mapTime;
+  return s;
+}
+
+// ref: HMM.cpp:1110-1177.  Runs on the output pipeline's threads; reads only immutable members.
+void HMM::formatSegments(const SegmentBlock& block, const size_t lo, const size_t hi, std::string& out) const
+{
+  const bool bin = decodingParams.BIN_OUT;
+  out.reserve(out.size() + (hi - lo) * (bin ? 40 : 96));
+  char chr[16];
+  const size_t chrLen = static_cast<size_t>(std::to_chars(chr, chr + sizeof chr, data.chrNumber).ptr - chr);
+  for (size_t i = lo; i < hi; ++i) {
+    const IbdSegment s = toIbdSegment(block, i);
+    const int bpStart = data.physicalPositions[s.posStart], bpEnd = data.physicalPositions[s.posEnd];
+    const float cm = 100.f * (data.geneticPositions[s.posEnd] - data.geneticPositions[s.posStart]);
+    const double score = s.prob / static_cast<double>(static_cast<unsigned>(s.posEnd - s.posStart) + 1u);
+    if (!bin) {
+      out += m_out->idPrefix[s.ind1];
+      out += static_cast<char>('0' + s.hap1);
+      out += '\t';
+      out += m_out->idPrefix[s.ind2];
+      out += static_cast<char>('0' + s.hap2);
+      out += '\t';
+      out.append(chr, chrLen);
+      out += '\t';
+      appendInt(out, bpStart);
+      out += '\t';
+      appendInt(out, bpEnd);
+      if (decodingParams.outputIbdSegmentLength) {
+        appendG7(out, static_cast<double>(cm));
+      }
+      appendG7(out, score);
+      if (decodingParams.doPerPairPosteriorMean) {
+        appendG7(out, static_cast<double>(s.postMean));
+      }
+      if (decodingParams.doPerPairMAP) {
+        appendG7(out, static_cast<double>(s.mapTime));
+      }
+      out += '\n';
+    } else {
+      auto put = [&out](const void* p, const size_t nBytes) { out.append(static_cast<const char*>(p), nBytes); };
+      const unsigned ind[2] = {s.ind1, s.ind2};
+      const uint8_t hp[2] = {static_cast<uint8_t>(s.hap1), static_cast<uint8_t>(s.hap2)};
+      const float scoreF = static_cast<float>(score);
+      put(&ind[0], sizeof(unsigned));
+      put(&hp[0], 1);
+      put(&ind[1], sizeof(unsigned));
+      put(&hp[1], 1);
+      put(&bpStart, sizeof(int));
+      put(&bpEnd, sizeof(int));
+      if (decodingParams.outputIbdSegmentLength) {
+        put(&cm, sizeof(float));
+      }
+      put(&scoreF, sizeof(float));
+      if (decodingParams.doPerPairPosteriorMean) {
+        put(&s.postMean, sizeof(float));
+      }
+      if (decodingParams.doPerPairMAP) {
+        put(&s.mapTime, sizeof(float));
+      }
     }
   }
 }

@@ -126,6 +126,7 @@ private:
     uint32_t hapA, hapB, from, to;
   };
   struct GzOut;
+  struct SegmentBlock;
 
   Data data;
   DecodingQuantities m_decodingQuant;
@@ -162,5 +163,7 @@ private:
   void flushPending(bool all);
   void runSegmentChunk(const Pending* pairs, size_t n);
   void runPerSiteChunk(const Pending* pairs, const unsigned long* rows, size_t n);
-  void writeSegment(const IbdSegment& s);
+  IbdSegment toIbdSegment(const SegmentBlock& block, size_t i) const;
+  void formatSegments(const SegmentBlock& block, size_t lo, size_t hi, std::string& out) const;
+  double m_segmentsPerPair = 4.0;  // densest chunk so far: sizes the next chunk's record buffer
 };

@@ -195,6 +195,8 @@ PYBIND11_MODULE(pyASMC, m)
       .def_readwrite("device", &DecodingParams::device)
       .def_readwrite("exactArithmetic", &DecodingParams::exactArithmetic)
       .def_readwrite("referenceCandidateOrder", &DecodingParams::referenceCandidateOrder)
+      .def_readwrite("outputCompressionLevel", &DecodingParams::outputCompressionLevel)
+      .def_readwrite("outputThreads", &DecodingParams::outputThreads)
       .def_readwrite("verbose", &DecodingParams::verbose);
 
   py::class_<IbdPairDataLine>(m, "IbdPairDataLine")
