@@ -215,10 +215,11 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
   if (S == 69 && narrow) {
     // 2 CTAs x 4 warps per SM at 255 registers: measured 12.2e9 pair-sites/s vs 10.1e9 at 3 CTAs / 168 registers (spills)
     const int rq = (m.stateThreshold + 1 + 3) / 4;
-    FastKernelFn fn = rq == 1   ? fsmc::decodeNarrowKernel<69, 1, kFastDepth, kFastRescale, 128, 2>
-                      : rq == 2 ? fsmc::decodeNarrowKernel<69, 2, kFastDepth, kFastRescale, 128, 2>
-                      : rq == 3 ? fsmc::decodeNarrowKernel<69, 3, kFastDepth, kFastRescale, 128, 2>
-                                : fsmc::decodeNarrowKernel<69, 4, kFastDepth, kFastRescale, 128, 2>;
+    // ring slots hold 4 window positions when two CTAs of that size fit an SM (records of up to 8 floats), else 2
+    FastKernelFn fn = rq == 1   ? fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2>
+                      : rq == 2 ? fsmc::decodeNarrowKernel<69, 2, 4, kFastDepth, 128, 2>
+                      : rq == 3 ? fsmc::decodeNarrowKernel<69, 3, 2, kFastDepth, 128, 2>
+                                : fsmc::decodeNarrowKernel<69, 4, 2, kFastDepth, 128, 2>;
     return FastChoice{fn, 72, 128, false, true, rq};
   }
   if (S == 69) {
@@ -231,8 +232,9 @@ size_t fastSmemBytes(const FastChoice& fc, const int S)
 {
   const size_t warps = fc.threads / 32;
   if (fc.narrow) {
-    return warps * kFastDepth * (static_cast<size_t>(fsmc::kNarrowMaxQuads) * 32 * 16 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4) +
-           warps * 2 * kFastDepth * sizeof(uint64_t);
+    const size_t group = fc.recordQuads <= 2 ? 4 : 2;
+    const size_t slot = group * static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4 + (group + 1) * static_cast<size_t>(fc.recordQuads) * 32 * 16;
+    return warps * kFastDepth * slot + warps * kFastDepth * sizeof(uint64_t);
   }
   return warps * (kFastDepth * (static_cast<size_t>(fc.Spad) * 32 * 4 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4) +
                   0 * static_cast<size_t>(S)) +

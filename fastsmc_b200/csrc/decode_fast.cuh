@@ -104,58 +104,82 @@ __device__ __forceinline__ float f4(const float4& v, const int j)
 // back edge (the in-place form cost 77 MOVs per warp-site, profiles/r1_v3_*).
 
 // x: beta(p+1) on entry (destroyed); y: unscaled beta(p) on return.  ref: HMM.cpp:957-1016
+//
+// The step is two first-order recurrences in opposite directions (BU descending, BL ascending), each a chain of S
+// dependent FMAs.  With two warps per scheduler a single chain leaves the FMA pipe idle for most of its 4-cycle
+// latency, so the state range is cut in the middle and the two chains always run at the same time on different halves:
+//   phase A: BU over the upper half (descending)  ||  BL over the lower half (ascending), partial results parked in y
+//   phase B: BU over the lower half (descending)  ||  BL over the upper half (ascending), each completing y
+// Same operations on the same operands as the one-chain-at-a-time form (bit-identical), same instruction count.
 template <int S> __device__ __forceinline__ void backwardStep(float (&x)[S], float (&y)[S], const float* row, const int cls)
 {
-  constexpr int SQ = (S + 3) / 4, Spad = SQ * 4;
+  constexpr int SQ = (S + 3) / 4, Spad = SQ * 4, QM = (SQ + 1) / 2;
   const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
   const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
   const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
   const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
   const float4* Rr = reinterpret_cast<const float4*>(row + 6 * Spad);
-  // vec = beta(p+1) * emission(p+1), in place in x
+  float bu = 0.f, bl = 0.f;
+  // phase A
 #pragma unroll
-  for (int q = 0; q < SQ; ++q) {
-    const float4 e4 = E[q];
+  for (int i = 0; i < QM; ++i) {
+    const int qu = SQ - 1 - i;
+    if (qu >= QM) {
+      const float4 e4 = E[qu], u4 = Ur[qu], r4 = Rr[qu];
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const int k = 4 * q + i;
-      if (k < S) {
-        x[k] *= f4(e4, i);
+      for (int j = 3; j >= 0; --j) {
+        const int k = 4 * qu + j;
+        if (k < S) {
+          x[k] *= f4(e4, j);  // vec = beta(p+1) * emission(p+1), in place
+          if (k == S - 1) {
+            y[k] = 0.f;
+          } else {
+            bu = fmaf(f4(r4, j), bu, f4(u4, j) * x[k + 1]);  // BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
+            y[k] = bu;
+          }
+        }
       }
     }
-  }
-  // y[k] = BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
-  {
-    float bu = 0.f;
+    {
+      const int ql = i;
+      const float4 e4 = E[ql], d4 = Dr[ql], b4 = Br[ql];
 #pragma unroll
-    for (int q = SQ - 1; q >= 0; --q) {
-      const float4 u4 = Ur[q];
-      const float4 r4 = Rr[q];
-#pragma unroll
-      for (int i = 3; i >= 0; --i) {
-        const int k = 4 * q + i;
-        if (k == S - 1) {
-          y[k] = 0.f;
-        } else if (k < S - 1) {
-          bu = fmaf(f4(r4, i), bu, f4(u4, i) * x[k + 1]);
-          y[k] = bu;
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * ql + j;
+        if (k < S) {
+          x[k] *= f4(e4, j);
+          y[k] = fmaf(f4(d4, j), x[k], bl);  // BL[k] + D[k] vec[k], BL[k] = sum_{j<k} B[j] vec[j]
+          bl = fmaf(f4(b4, j), x[k], bl);
         }
       }
     }
   }
-  // y[k] = beta(p)[k] = BL + D[k] vec[k] + BU[k], BL += B[k-1] vec[k-1]
-  {
-    float bl = 0.f;
+  // phase B
 #pragma unroll
-    for (int q = 0; q < SQ; ++q) {
-      const float4 d4 = Dr[q];
-      const float4 b4 = Br[q];
+  for (int i = 0; i < QM; ++i) {
+    {
+      const int ql = QM - 1 - i;
+      const float4 u4 = Ur[ql], r4 = Rr[ql];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = 4 * q + i;
+      for (int j = 3; j >= 0; --j) {
+        const int k = 4 * ql + j;
+        if (k < S - 1) {
+          bu = fmaf(f4(r4, j), bu, f4(u4, j) * x[k + 1]);
+          y[k] += bu;
+        } else if (k == S - 1) {
+          // (only when the whole vector is one quad wide)
+        }
+      }
+    }
+    const int qu = QM + i;
+    if (qu < SQ) {
+      const float4 d4 = Dr[qu], b4 = Br[qu];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * qu + j;
         if (k < S) {
-          y[k] = fmaf(f4(d4, i), x[k], bl) + y[k];
-          bl = fmaf(f4(b4, i), x[k], bl);
+          y[k] = fmaf(f4(d4, j), x[k], bl) + y[k];
+          bl = fmaf(f4(b4, j), x[k], bl);
         }
       }
     }
@@ -183,44 +207,69 @@ template <int S> __device__ __forceinline__ void scaleStates(float (&a)[S], cons
   }
 }
 
-// x: alpha(p-1) on entry; y: unscaled alpha(p) on return (x is left holding the suffix sums).  Returns
-// sum_k alpha(p-1)[k], the normaliser of the previous site, for free.  ref: HMM.cpp:799-830
+// x: alpha(p-1) on entry; y: unscaled alpha(p) on return.  Returns sum_k alpha(p-1)[k], the normaliser of the previous
+// site, for free.  ref: HMM.cpp:799-830.  Two chains (AU ascending, the suffix sums of x descending) run at the same
+// time on different halves of the state range, like backwardStep:
+//   phase A: y[k] = AU[k] + D[k] x[k] over the lower half  ||  y[k] = sum_{j>k} x[j] over the upper half
+//   phase B: y[k] = E[k] (AU[k] + D[k] x[k] + B[k] y[k]) over the upper half  ||  y[k] = E[k] (y[k] + B[k] run) over the lower
 template <int S>
 __device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[S], float (&y)[S], const float* row, const int cls)
 {
-  constexpr int SQ = (S + 3) / 4, Spad = SQ * 4;
+  constexpr int SQ = (S + 3) / 4, Spad = SQ * 4, QM = (SQ + 1) / 2;
+  static_assert(4 * QM < S, "the upper half holds the last state");
   const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
   const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
   const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
   const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
-  // ascending pass 1: y[k] = AU[k] + D[k] x[k]  with  AU[k] = U[k-1] x[k-1] + colRatio[k-1] AU[k-1]
-  {
-    float au = 0.f;
+  float au = 0.f, run = 0.f;
+  // phase A
 #pragma unroll
-    for (int q = 0; q < SQ; ++q) {
-      const float4 d4 = Dr[q];
-      const float4 u4 = Ur[q];
+  for (int i = 0; i < QM; ++i) {
+    {
+      const int ql = i;
+      const float4 d4 = Dr[ql], u4 = Ur[ql];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const int k = 4 * q + i;
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * ql + j;
+        y[k] = fmaf(f4(d4, j), x[k], au);                   // AU[k] + D[k] x[k]
+        au = fmaf(colRatios[k], au, f4(u4, j) * x[k]);      // AU[k+1] = U[k] x[k] + colRatio[k] AU[k]
+      }
+    }
+    const int qu = SQ - 1 - i;
+    if (qu >= QM) {
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        const int k = 4 * qu + j;
         if (k < S) {
-          y[k] = fmaf(f4(d4, i), x[k], au);
-          au = fmaf(colRatios[k], au, f4(u4, i) * x[k]);
+          y[k] = run;
+          run += x[k];
         }
       }
     }
   }
-  // descending pass 2: run = sum_{j>k} x[j];  y[k] = E[k] (y[k] + B[k] run)
-  float run = 0.f;
+  // phase B
 #pragma unroll
-  for (int q = SQ - 1; q >= 0; --q) {
-    const float4 e4 = E[q];
-    const float4 b4 = Br[q];
+  for (int i = 0; i < QM; ++i) {
+    const int qu = QM + i;
+    if (qu < SQ) {
+      const float4 d4 = Dr[qu], u4 = Ur[qu], e4 = E[qu], b4 = Br[qu];
 #pragma unroll
-    for (int i = 3; i >= 0; --i) {
-      const int k = 4 * q + i;
-      if (k < S) {
-        y[k] = f4(e4, i) * (k < S - 1 ? fmaf(f4(b4, i), run, y[k]) : y[k]);
+      for (int j = 0; j < 4; ++j) {
+        const int k = 4 * qu + j;
+        if (k < S) {
+          const float t = fmaf(f4(d4, j), x[k], au);
+          y[k] = f4(e4, j) * (k < S - 1 ? fmaf(f4(b4, j), y[k], t) : t);
+          au = fmaf(colRatios[k], au, f4(u4, j) * x[k]);
+        }
+      }
+    }
+    {
+      const int ql = QM - 1 - i;
+      const float4 e4 = E[ql], b4 = Br[ql];
+#pragma unroll
+      for (int j = 3; j >= 0; --j) {
+        const int k = 4 * ql + j;
+        y[k] = f4(e4, j) * fmaf(f4(b4, j), run, y[k]);
         run += x[k];
       }
     }
@@ -242,40 +291,57 @@ __device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[
 // S=69, sT<=3.  The kernel becomes issue-bound.
 // -------------------------------------------------------------------------------------------------------------------
 constexpr int kNarrowMaxQuads = 4;  // record = up to 16 floats: sT <= 15
+constexpr int kNarrowGroup = 4;     // window positions per ring slot (one bulk copy and one barrier per group)
 
-template <int S_T, int RQ, int DEPTH, int RESCALE, int THREADS, int MIN_BLOCKS>
+// Ring slot of one warp: G coefficient rows followed by G+1 records (the extra record is the all-ones beta of the
+// window's last site, which rides with the first group of the backward sweep).
+template <int S_T, int RQ, int G> struct NarrowSlot {
+  static constexpr int SQ = (S_T + 3) / 4, Spad = SQ * 4;
+  static constexpr uint32_t kCoefBytes = kRowArrays * Spad * 4;
+  static constexpr uint32_t kRecBytes = RQ * 32 * 16;
+  static constexpr uint32_t kBytes = G * kCoefBytes + (G + 1) * kRecBytes;
+};
+
+// Site loop: positions are handled in groups of G.  Per group the elected lane waits once on the slot's mbarrier,
+// and issues one bulk copy per array (coefficient rows are contiguous over consecutive sites, and so are the records
+// of consecutive positions in the slab), so the per-site cost outside the recurrences is the genotype class lookup,
+// the record (RQ shared-memory accesses) and the segment caller.  Rescaling happens at the last step of every full
+// group, i.e. every G-th site.
+template <int S_T, int RQ, int G, int DEPTH, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const FastModel fm, const DecodeArgs args)
 {
   constexpr int S = S_T;
   constexpr int SQ = (S + 3) / 4;
   constexpr int Spad = SQ * 4;
   constexpr int NR = 4 * RQ - 1;                     // beta entries of a record; entry NR is the scale divisor
-  constexpr uint32_t kRecBytes = RQ * 32 * 16;
+  using Slot = NarrowSlot<S_T, RQ, G>;
+  constexpr uint32_t kRecBytes = Slot::kRecBytes;
+  constexpr uint32_t kCoefBytes = Slot::kCoefBytes;
   constexpr size_t kRecFloats = static_cast<size_t>(RQ) * 32 * 4;
-  constexpr uint32_t kRecSlotBytes = kNarrowMaxQuads * 32 * 16;  // slots are sized for the largest record (parking area)
-  constexpr uint32_t kCoefBytes = kRowArrays * Spad * 4;
+  constexpr size_t kRowFloats = static_cast<size_t>(kRowArrays) * Spad;
   constexpr int kWarps = THREADS / 32;
-  constexpr size_t kWarpBytes = static_cast<size_t>(DEPTH) * (kRecSlotBytes + kCoefBytes);
+  constexpr size_t kWarpBytes = static_cast<size_t>(DEPTH) * Slot::kBytes;
   static_assert(S >= 4 * kNarrowMaxQuads && RQ >= 1 && RQ <= kNarrowMaxQuads, "record quads index the state vector");
+  static_assert(G % 2 == 0, "the two state vectors swap roles every step");
 
   extern __shared__ __align__(128) unsigned char smemRaw[];
   const DeviceModel m = fm.base;
   const int lane = threadIdx.x & 31;
   const int warp = threadIdx.x >> 5;
   unsigned char* mine = smemRaw + static_cast<size_t>(warp) * kWarpBytes;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + static_cast<size_t>(kWarps) * kWarpBytes) + warp * 2 * DEPTH;
-  auto recSlot = [&](const int i) { return reinterpret_cast<float4*>(mine + static_cast<size_t>(i) * kRecSlotBytes); };
-  auto coefSlot = [&](const int i) {
-    return reinterpret_cast<const float*>(mine + static_cast<size_t>(DEPTH) * kRecSlotBytes + static_cast<size_t>(i) * kCoefBytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + static_cast<size_t>(kWarps) * kWarpBytes) + warp * DEPTH;
+  auto coefArea = [&](const int slot) { return reinterpret_cast<float*>(mine + static_cast<size_t>(slot) * Slot::kBytes); };
+  auto recArea = [&](const int slot) {
+    return reinterpret_cast<float4*>(mine + static_cast<size_t>(slot) * Slot::kBytes + static_cast<size_t>(G) * kCoefBytes);
   };
   if (lane == 0) {
-    for (int i = 0; i < 2 * DEPTH; ++i) {
+    for (int i = 0; i < DEPTH; ++i) {
       mbarInit(&bars[i], 1);
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   __syncwarp();
-  uint32_t recParity = 0, coefParity = 0;
+  uint32_t parity = 0;  // bit i = parity the next wait on slot i expects
 
   const unsigned flags = args.flags;
   const bool wantSeg = flags & FSMC_CALL_SEGMENTS;
@@ -305,7 +371,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
     PairBits bits;
     bits.a = m.haps + static_cast<size_t>(args.hapA[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
     bits.b = m.haps + static_cast<size_t>(args.hapB[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
-    const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowArrays * Spad;
+    const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowFloats;
 
     float a[S], c[S];
     float acc[NR];
@@ -314,13 +380,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
       acc[k] = 0.f;
     }
 
-    // stage (beta^[k < sT], 0.., scale divisor) of window position p and hand it to the copy engine
-    auto storeRecord = [&](const float (&v)[S], const int p, const int bslot, const float divisor) {
-      if (lane == 0) {
-        bulkWaitRead<DEPTH - 1>();
-      }
-      __syncwarp();
-      float4* out = recSlot(bslot);
+    // (beta^[k < sT], 0.., scale divisor) of one window position into a staging record
+    auto stageRecord = [&](const float (&v)[S], float4* out, const float divisor) {
 #pragma unroll
       for (int q = 0; q < RQ; ++q) {
         float w[4];
@@ -331,58 +392,87 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
         }
         out[q * 32 + lane] = make_float4(w[0], w[1], w[2], w[3]);
       }
-      fenceProxyAsync();
-      __syncwarp();
-      if (lane == 0) {
-        bulkStore(slab + static_cast<size_t>(p) * kRecFloats, out, kRecBytes);
-        bulkCommit();
-      }
     };
 
     // ---- sweep 1: backward.  Step j handles window position len-2-j with the coefficient row of len-1-j ------------
     {
-      auto prefetchCoef = [&](const int j) {
+      const int steps = len - 1;
+      const int nGroups = (steps + G - 1) / G;
+      auto prefetch = [&](const int g) {  // rows of steps [gG, gG+n): window positions [len-j1, len-j0), ascending
         if (lane == 0) {
-          uint64_t* bar = &bars[DEPTH + j % DEPTH];
-          mbarExpectTx(bar, kCoefBytes);
-          bulkLoad(const_cast<float*>(coefSlot(j % DEPTH)), rowBase + static_cast<size_t>(len - 1 - j) * kRowArrays * Spad,
-                   kCoefBytes, bar);
+          const int j0 = g * G, j1 = min(steps, j0 + G);
+          const int slot = g % DEPTH;
+          const uint32_t bytes = static_cast<uint32_t>(j1 - j0) * kCoefBytes;
+          mbarExpectTx(&bars[slot], bytes);
+          bulkLoad(coefArea(slot), rowBase + static_cast<size_t>(len - j1) * kRowFloats, bytes, &bars[slot]);
         }
       };
-      const int steps = len - 1;
-      for (int j = 0; j < DEPTH && j < steps; ++j) {
-        prefetchCoef(j);
+      for (int g = 0; g < DEPTH && g < nGroups; ++g) {
+        prefetch(g);
       }
 #pragma unroll
       for (int k = 0; k < S; ++k) {
         a[k] = 1.f;
       }
-      storeRecord(a, len - 1, 0, 1.0f);
-      auto step = [&](const int j, float (&x)[S], float (&y)[S]) {
-        const int p = len - 2 - j;
-        const int slot = j % DEPTH;
-        const int cls = bits.cls(from + p + 1);
-        mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
-        coefParity ^= 1u << slot;
-        backwardStep<S>(x, y, coefSlot(slot), cls);
+      if (nGroups == 0) {
+        // single-site window: only the all-ones record
+        stageRecord(a, recArea(0), 1.0f);
+        fenceProxyAsync();
         __syncwarp();
-        if (j + DEPTH < steps) {
-          prefetchCoef(j + DEPTH);
+        if (lane == 0) {
+          bulkStore(slab, recArea(0), kRecBytes);
+          bulkCommit();
         }
-        float divisor = 1.0f;
-        if ((p & (RESCALE - 1)) == 0) {
-          divisor = sumStates<S>(y);
-          scaleStates<S>(y, 1.0f / divisor);
-        }
-        storeRecord(y, p, (j + 1) % DEPTH, divisor);
-      };
-      int j = 0;
-      for (; j + 1 < steps; j += 2) {
-        step(j, a, c);
-        step(j + 1, c, a);
       }
-      if (j < steps) {
-        step(j, a, c);  // beta^ of the first site ends in c
+      for (int g = 0; g < nGroups; ++g) {
+        const int slot = g % DEPTH;
+        const int j0 = g * G;
+        const int n = min(G, steps - j0);
+        const float* coef = coefArea(slot);
+        float4* stage = recArea(slot);
+        if (lane == 0) {
+          bulkWaitRead<DEPTH - 1>();  // the store that last read this slot's staging records has drained them
+        }
+        mbarWait(&bars[slot], (parity >> slot) & 1u);
+        parity ^= 1u << slot;
+        __syncwarp();
+        if (g == 0) {
+          stageRecord(a, stage + static_cast<size_t>(n) * RQ * 32, 1.0f);  // position len-1
+        }
+        auto step = [&](const int i, float (&x)[S], float (&y)[S], const bool rescale) {
+          const int p = len - 2 - (j0 + i);
+          const int cls = bits.cls(from + p + 1);
+          backwardStep<S>(x, y, coef + static_cast<size_t>(n - 1 - i) * kRowFloats, cls);
+          float divisor = 1.0f;
+          if (rescale) {
+            divisor = sumStates<S>(y);
+            scaleStates<S>(y, 1.0f / divisor);
+          }
+          stageRecord(y, stage + static_cast<size_t>(n - 1 - i) * RQ * 32, divisor);
+        };
+#pragma unroll
+        for (int i = 0; i < G; i += 2) {
+          if (i < n) {
+            step(i, a, c, false);
+          }
+          if (i + 1 < n) {
+            step(i + 1, c, a, i + 1 == G - 1);
+          }
+        }
+        fenceProxyAsync();
+        __syncwarp();  // every lane is done with the coefficient rows and has staged its records
+        if (lane == 0) {
+          const int j1 = j0 + n;
+          bulkStore(slab + static_cast<size_t>(len - 1 - j1) * kRecFloats, stage,
+                    static_cast<uint32_t>(n + (g == 0 ? 1 : 0)) * kRecBytes);
+          bulkCommit();
+        }
+        if (g + DEPTH < nGroups) {
+          prefetch(g + DEPTH);
+        }
+      }
+      if (steps & 1) {
+        // beta^ of the first site ended in c
       } else {
 #pragma unroll
         for (int k = 0; k < S; ++k) {
@@ -397,33 +487,30 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
 
     // ---- sweep 2: forward + consumers ---------------------------------------------------------------------------------
     {
-      auto prefetch = [&](const int p) {
+      const int nGroups = (len + G - 1) / G;
+      auto prefetch = [&](const int g) {
         if (lane == 0) {
-          const int slot = p % DEPTH;
-          mbarExpectTx(&bars[slot], kRecBytes);
-          bulkLoad(recSlot(slot), slab + static_cast<size_t>(p) * kRecFloats, kRecBytes, &bars[slot]);
-          mbarExpectTx(&bars[DEPTH + slot], kCoefBytes);
-          bulkLoad(const_cast<float*>(coefSlot(slot)), rowBase + static_cast<size_t>(p) * kRowArrays * Spad, kCoefBytes,
-                   &bars[DEPTH + slot]);
+          const int p0 = g * G;
+          const uint32_t n = static_cast<uint32_t>(min(G, len - p0));
+          const int slot = g % DEPTH;
+          mbarExpectTx(&bars[slot], n * (kCoefBytes + kRecBytes));
+          bulkLoad(coefArea(slot), rowBase + static_cast<size_t>(p0) * kRowFloats, n * kCoefBytes, &bars[slot]);
+          bulkLoad(recArea(slot), slab + static_cast<size_t>(p0) * kRecFloats, n * kRecBytes, &bars[slot]);
         }
       };
-      for (int p = 0; p < DEPTH && p < len; ++p) {
-        prefetch(p);
+      for (int g = 0; g < DEPTH && g < nGroups; ++g) {
+        prefetch(g);
       }
       CallerState cs;
       float Z = 1.f, bPrev = 1.f;
 
-      // consumers of window position p; v = alpha^(p)
-      auto consume = [&](const int p, const float (&v)[S]) {
+      // consumers of window position p; v = alpha^(p); rec = this position's record (parking area once drained)
+      auto consume = [&](const int p, const float (&v)[S], float4* rec) {
         const int site = from + p;
-        const int slot = p % DEPTH;
-        mbarWait(&bars[slot], (recParity >> slot) & 1u);
-        recParity ^= 1u << slot;
-        const float4* R4 = recSlot(slot);
         float q[4 * RQ];  // alpha^[k] beta^[k] for k < sT (0 above); q[NR] = b_p
 #pragma unroll
         for (int qq = 0; qq < RQ; ++qq) {
-          const float4 r4 = R4[qq * 32 + lane];
+          const float4 r4 = rec[qq * 32 + lane];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             q[4 * qq + i] = f4(r4, i);
@@ -443,24 +530,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
         }
         const bool inScan = wantSeg && site >= scanFrom && site < scanTo;
         if (inScan) {
-          int now = -1;
-          if (ibd >= m.thr[0]) {
-            now = 0;
-          } else if (ibd >= m.thr[1]) {
-            now = 1;
-          } else if (ibd >= m.thr[2]) {
-            now = 2;
-          } else if (ibd >= m.thr[3]) {
-            now = 3;
-          }
+          int now = ibd >= m.thr[0] ? 0 : (ibd >= m.thr[1] ? 1 : (ibd >= m.thr[2] ? 2 : (ibd >= m.thr[3] ? 3 : -1)));
           if (!laneActive) {
             now = -1;
           }
           const bool changed = now != cs.level;
           const bool ending = changed && cs.level >= 0;
           const bool closing = now >= 0 && site == scanTo - 1;
-          float* park = reinterpret_cast<float*>(recSlot(slot)) + lane;  // drained record slot: [k][32], k < 15
-          if (__any_sync(kFull, ending)) {
+          const float rr = now >= 0 ? r : 0.f;
+          const float keep = changed ? 0.f : 1.f;
+          if (__any_sync(kFull, ending || closing)) {
+            // rare: a run ends at site-1 and/or the scan window closes on a live run
+            float* park = reinterpret_cast<float*>(rec) + lane;  // drained record: [k][32], k < NR
+            __syncwarp();
             if (wantAge) {
 #pragma unroll
               for (int k = 0; k < NR; ++k) {
@@ -472,19 +554,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
               emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, park, wantAge);
             }
             __syncwarp();
-          }
-          if (wantAge) {
-            const float rr = now >= 0 ? r : 0.f;
-            const float keep = changed ? 0.f : 1.f;
-#pragma unroll
-            for (int k = 0; k < NR; ++k) {
-              acc[k] = fmaf(q[k], rr, keep * acc[k]);
-            }
-          }
-          if (__any_sync(kFull, closing)) {
             if (wantAge) {
 #pragma unroll
               for (int k = 0; k < NR; ++k) {
+                acc[k] = fmaf(q[k], rr, keep * acc[k]);
                 park[k * 32] = acc[k];
               }
               __syncwarp();
@@ -493,72 +566,76 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
               emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, park, wantAge);
             }
             __syncwarp();
-          }
-          if (now >= 0) {
-            cs.prob = changed ? ibd : cs.prob + ibd;
-            if (changed) {
-              cs.start = site;
+          } else if (wantAge) {
+#pragma unroll
+            for (int k = 0; k < NR; ++k) {
+              acc[k] = fmaf(q[k], rr, keep * acc[k]);
             }
-            if (closing) {
-              cs.prob = 0.f;
-            }
-          } else {
-            cs.prob = 0.f;
           }
+          cs.prob = (now >= 0 && !closing) ? (changed ? ibd : cs.prob + ibd) : 0.f;
+          cs.start = (now >= 0 && changed) ? site : cs.start;
           cs.level = now;
-        }
-        __syncwarp();
-        if (p + DEPTH < len) {
-          prefetch(p + DEPTH);
         }
       };
 
-      // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
-      {
-        const int cls = bits.cls(from);
-        mbarWait(&bars[DEPTH], coefParity & 1u);
-        coefParity ^= 1u;
-        const float4* E = reinterpret_cast<const float4*>(coefSlot(0) + cls * Spad);
-        float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
-#pragma unroll
-        for (int q = 0; q < SQ; ++q) {
-          const float4 e4 = E[q];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) {
-            const int k = 4 * q + i;
-            if (k < S) {
-              a[k] = fm.prior[k] * f4(e4, i);
-            }
+      for (int g = 0; g < nGroups; ++g) {
+        const int slot = g % DEPTH;
+        const int p0 = g * G;
+        const int n = min(G, len - p0);
+        const float* coef = coefArea(slot);
+        float4* recs = recArea(slot);
+        mbarWait(&bars[slot], (parity >> slot) & 1u);
+        parity ^= 1u << slot;
+        auto step = [&](const int i, float (&x)[S], float (&y)[S], const bool rescale) {
+          const int p = p0 + i;
+          const int cls = bits.cls(from + p);
+          const float total = forwardStep<S>(fm.colRatios, x, y, coef + static_cast<size_t>(i) * kRowFloats, cls);
+          float sc = 1.0f;
+          if (rescale) {
+            sc = 1.0f / total;
+            scaleStates<S>(y, sc);
           }
-          z0 = fmaf(a[4 * q], c[4 * q], z0);
-          if (4 * q + 1 < S) z1 = fmaf(a[4 * q + 1], c[4 * q + 1], z1);
-          if (4 * q + 2 < S) z2 = fmaf(a[4 * q + 2], c[4 * q + 2], z2);
-          if (4 * q + 3 < S) z3 = fmaf(a[4 * q + 3], c[4 * q + 3], z3);
+          Z *= bPrev * sc;  // Z_p = Z_{p-1} * b_{p-1} / a_p
+          consume(p, y, recs + static_cast<size_t>(i) * RQ * 32);
+        };
+        if (g == 0) {
+          // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
+          const int cls = bits.cls(from);
+          const float4* E = reinterpret_cast<const float4*>(coef + cls * Spad);
+          float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll
+          for (int q = 0; q < SQ; ++q) {
+            const float4 e4 = E[q];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+              const int k = 4 * q + i;
+              if (k < S) {
+                a[k] = fm.prior[k] * f4(e4, i);
+              }
+            }
+            z0 = fmaf(a[4 * q], c[4 * q], z0);
+            if (4 * q + 1 < S) z1 = fmaf(a[4 * q + 1], c[4 * q + 1], z1);
+            if (4 * q + 2 < S) z2 = fmaf(a[4 * q + 2], c[4 * q + 2], z2);
+            if (4 * q + 3 < S) z3 = fmaf(a[4 * q + 3], c[4 * q + 3], z3);
+          }
+          Z = (z0 + z1) + (z2 + z3);
+          consume(0, a, recs);
+        } else {
+          step(0, c, a, false);
         }
-        Z = (z0 + z1) + (z2 + z3);
-        consume(0, a);
-      }
-      auto step = [&](const int p, float (&x)[S], float (&y)[S]) {
-        const int slot = p % DEPTH;
-        const int cls = bits.cls(from + p);
-        mbarWait(&bars[DEPTH + slot], (coefParity >> slot) & 1u);
-        coefParity ^= 1u << slot;
-        const float total = forwardStep<S>(fm.colRatios, x, y, coefSlot(slot), cls);
-        float sc = 1.0f;
-        if ((p & (RESCALE - 1)) == 0) {
-          sc = 1.0f / total;
-          scaleStates<S>(y, sc);
+#pragma unroll
+        for (int i = 1; i < G; i += 2) {
+          if (i < n) {
+            step(i, a, c, i == G - 1);
+          }
+          if (i + 1 < G && i + 1 < n) {
+            step(i + 1, c, a, false);
+          }
         }
-        Z *= bPrev * sc;  // Z_p = Z_{p-1} * b_{p-1} / a_p
-        consume(p, y);
-      };
-      int p = 1;
-      for (; p + 1 < len; p += 2) {
-        step(p, a, c);
-        step(p + 1, c, a);
-      }
-      if (p < len) {
-        step(p, a, c);
+        __syncwarp();  // the slot is drained (its records double as the parking area above)
+        if (g + DEPTH < nGroups) {
+          prefetch(g + DEPTH);
+        }
       }
     }
     __syncwarp();
