@@ -22,6 +22,7 @@ SITE_IBD = 0x10
 EXACT = 0x20
 GENERIC_KERNEL = 0x40
 WIDE_KERNEL = 0x80
+ONE_WARP_KERNEL = 0x100
 
 E_OVERFLOW = -4
 
@@ -59,7 +60,7 @@ class Stats(C.Structure):
     _fields_ = [
         ("numSegments", C.c_int64), ("pairSites", C.c_double), ("kernelMs", C.c_float), ("totalMs", C.c_float),
         ("kernelLaunches", C.c_int32), ("statesKernel", C.c_int32), ("scratchBytes", C.c_int64),
-        ("narrowKernel", C.c_int32), ("reserved", C.c_int32),
+        ("narrowKernel", C.c_int32), ("tileWarps", C.c_int32),
     ]
 
 

@@ -52,14 +52,26 @@ def _sources(*dirs, exts=(".cu", ".cuh", ".cpp", ".hpp", ".h")):
 
 
 def build_device(force=False, verbose=False):
-    """libfastsmc_b200.so: CUDA kernels + the C ABI of include/fastsmc_b200.h."""
+    """libfastsmc_b200.so: CUDA kernels + the C ABI of include/fastsmc_b200.h.  Every .cu under csrc/ is one
+    translation unit; they compile concurrently and are linked into one shared library."""
     os.makedirs(LIBDIR, exist_ok=True)
+    objdir = os.path.join(LIBDIR, "obj")
+    os.makedirs(objdir, exist_ok=True)
     target = os.path.join(LIBDIR, "libfastsmc_b200.so")
-    srcs = [os.path.join(CSRC, "capi.cu")]
+    srcs = sorted(os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith(".cu"))
     deps = _sources(CSRC, os.path.join(ROOT, "include"))
     if force or _newer(target, deps):
-        cmd = [_nvcc(), "-ccbin", _host_cxx()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", target] + srcs
-        subprocess.check_call(cmd)
+        flags = [f for f in NVCC_FLAGS if f != "-shared"] + (["-Xptxas", "-v"] if verbose else [])
+        procs = []
+        for src in srcs:
+            obj = os.path.join(objdir, os.path.basename(src)[:-3] + ".o")
+            procs.append((src, subprocess.Popen([_nvcc(), "-ccbin", _host_cxx()] + flags + ["-c", "-o", obj, src])))
+        failed = [src for src, pr in procs if pr.wait() != 0]
+        if failed:
+            raise RuntimeError("nvcc failed on " + ", ".join(failed))
+        objs = [os.path.join(objdir, os.path.basename(src)[:-3] + ".o") for src in srcs]
+        subprocess.check_call([_nvcc(), "-ccbin", _host_cxx(), "-gencode", "arch=compute_100a,code=sm_100a", "-shared",
+                               "-o", target] + objs)
     return target
 
 

@@ -14,6 +14,7 @@
 #include "decode_kernels.cuh"
 #include "decode_fast.cuh"
 #include "seed_kernels.cuh"
+#include "split_select.h"
 
 namespace
 {
@@ -153,6 +154,8 @@ struct fsmc_plan {
   int launches = 0;
   bool fast = false;  // decodeFastKernel / decodeNarrowKernel (decode_fast.cuh)
   bool narrow = false;
+  int tileWarps = 1;
+  int tilesPerBlock = 1;  // tiles in flight per CTA (= scratch slabs per CTA)
 };
 
 namespace
@@ -190,7 +193,7 @@ KernelChoice chooseKernel(const int S, const unsigned flags)
 }
 
 // The production kernel (decode_fast.cuh) exists for the state counts whose two state vectors fit the register file.
-typedef void (*FastKernelFn)(const fsmc::FastModel, const DecodeArgs);
+using fsmc::FastKernelFn;
 constexpr int kFastDepth = 2, kFastRescale = 4;
 struct FastChoice {
   FastKernelFn fn = nullptr;
@@ -199,7 +202,17 @@ struct FastChoice {
   bool acc = false;
   bool narrow = false;      // decodeNarrowKernel: sT+1 floats per pair-site in HBM instead of S
   int recordQuads = 0;
+  int splitWarps = 0;       // > 0: decodeSplitKernel, one tile per CTA of this many warps (decode_split.cuh)
+  size_t splitSmem = 0;
 };
+
+// FSMC_SPLIT=0 forces the one-warp-per-tile kernels, FSMC_SPLIT=1 the state-split kernels wherever one exists
+// (development / A-B measurements); unset = the faster of the two as measured on B200.
+int splitPreference()
+{
+  const char* e = std::getenv("FSMC_SPLIT");
+  return e && *e ? std::atoi(e) : -1;
+}
 // Without per-segment age estimates 8 warps (2 CTAs of 4) fit an SM; the accumulators of FSMC_SEG_AGE cost 8.6 KB of
 // shared memory per warp, which leaves room for 7 warps (1 CTA).
 FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
@@ -212,6 +225,21 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
   // only states below the IBD time threshold are looked at: no beta round trip needed
   const bool narrow = !(flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP | FSMC_WIDE_KERNEL)) && (!acc || m.ageThreshold <= m.stateThreshold) &&
                       m.stateThreshold + 1 <= 4 * fsmc::kNarrowMaxQuads;
+  const int rqWanted = narrow ? (m.stateThreshold + 1 + 3) / 4 : 0;
+  const int pref = (flags & FSMC_ONE_WARP_KERNEL) ? 0 : splitPreference();
+  const bool trySplit = pref == 1 || (pref == -1 && S == 159);
+  if (trySplit && (S == 69 || S == 159) && m.stateThreshold <= 32) {
+    fsmc::SplitChoice sc = S == 69 ? fsmc::splitKernel69(rqWanted, acc) : fsmc::splitKernel159(rqWanted, acc);
+    if (!sc.fn && narrow) {
+      sc = S == 69 ? fsmc::splitKernel69(0, acc) : fsmc::splitKernel159(0, acc);  // no such record width: full rows
+    }
+    if (sc.fn) {
+      FastChoice fc{sc.fn, sc.Spad, sc.warps * 32, sc.acc, sc.recordQuads > 0, sc.recordQuads};
+      fc.splitWarps = sc.warps;
+      fc.splitSmem = sc.smemBytes;
+      return fc;
+    }
+  }
   if (S == 69 && narrow) {
     // 2 CTAs x 4 warps per SM at 255 registers: measured 12.2e9 pair-sites/s vs 10.1e9 at 3 CTAs / 168 registers (spills)
     const int rq = (m.stateThreshold + 1 + 3) / 4;
@@ -230,6 +258,9 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
 }
 size_t fastSmemBytes(const FastChoice& fc, const int S)
 {
+  if (fc.splitWarps > 0) {
+    return fc.splitSmem;
+  }
   const size_t warps = fc.threads / 32;
   if (fc.narrow) {
     const size_t group = fc.recordQuads <= 2 ? 4 : 2;
@@ -563,8 +594,10 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   plan->fast = fc.fn != nullptr;
   plan->statesKernel = plan->fast ? m.S : kc.statesKernel;
   plan->narrow = fc.narrow;
+  plan->tileWarps = fc.splitWarps > 0 ? fc.splitWarps : 1;
   plan->mode = kc.mode;
-  int warpsPerBlock = (plan->fast ? fc.threads : kc.threads) / 32;
+  // tiles in flight per CTA: one per warp, except for the state-split kernels (one tile per CTA)
+  int warpsPerBlock = fc.splitWarps > 0 ? 1 : (plan->fast ? fc.threads : kc.threads) / 32;
   const size_t smemLimit = ctx->prop.sharedMemPerBlockOptin;
   int blocksPerSm = 0;
   if (plan->fast) {
@@ -616,6 +649,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   }
 
   plan->blocks = static_cast<int>(blocks);
+  plan->tilesPerBlock = warpsPerBlock;
   guard.keep = true;
   *out = plan;
   return FSMC_OK;
@@ -767,7 +801,8 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
     stats->kernelLaunches = plan->launches;
     stats->statesKernel = plan->statesKernel;
     stats->narrowKernel = plan->narrow ? 1 : 0;
-    stats->scratchBytes = static_cast<int64_t>(plan->scratchPerWarp) * sizeof(float) * plan->blocks * (plan->threads / 32);
+    stats->tileWarps = plan->tileWarps;
+    stats->scratchBytes = static_cast<int64_t>(plan->scratchPerWarp) * sizeof(float) * plan->blocks * plan->tilesPerBlock;
   }
   plan->launched = false;
   return rc;

@@ -576,7 +576,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeTilesKernel(const D
 // E_homMajor = e1 + e0m1, E_het = e1, E_homMinor = (e1 + e0m1) + e2m0 are bit-identical to the
 // reference's e1 + e0m1*isZero + e2m0*isTwo for the three genotype classes (ref HMM.cpp:827-828).
 // -------------------------------------------------------------------------------------------------
-__global__ void buildSiteRowsKernel(const int S, const int Spad, const int L, const float* __restrict__ e1,
+static __global__ void buildSiteRowsKernel(const int S, const int Spad, const int L, const float* __restrict__ e1,
                                     const float* __restrict__ e0m1, const float* __restrict__ e2m0,
                                     const float* __restrict__ D, const float* __restrict__ B,
                                     const float* __restrict__ U, const float* __restrict__ RR,

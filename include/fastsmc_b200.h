@@ -108,6 +108,7 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, int64_t numHaps, in
                                   /* results are bit-identical to the reference's NO_SSE build    */
 #define FSMC_GENERIC_KERNEL 0x40u /* force the any-S shared-memory kernel (testing)               */
 #define FSMC_WIDE_KERNEL 0x80u    /* never use the narrow (no beta round trip) kernel (testing)   */
+#define FSMC_ONE_WARP_KERNEL 0x100u /* never use the state-split kernels (one tile per CTA) (testing) */
 
 typedef struct fsmc_segment {
   uint32_t pair;     /* tile * 32 + lane                                                        */
@@ -150,7 +151,7 @@ typedef struct fsmc_decode_stats {
   int32_t statesKernel; /* S the kernel was specialised for, 0 = generic                          */
   int64_t scratchBytes; /* backward-sweep scratch in HBM                                          */
   int32_t narrowKernel; /* 1 if the kernel without the beta round trip ran (states < threshold only) */
-  int32_t reserved;
+  int32_t tileWarps;    /* warps that shared a tile: 1, or 2 / 4 for the state-split kernels                */
 } fsmc_decode_stats;
 
 int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats* stats);

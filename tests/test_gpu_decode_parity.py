@@ -170,7 +170,14 @@ def synthetic69(oracle_mod, tmp_path_factory):
     return o, ctx
 
 
-def test_fast_kernel_per_site_outputs_69_states(synthetic69):
+@pytest.fixture(params=[0, 1], ids=["one-warp", "split"])
+def split(request, monkeypatch):
+    """FSMC_SPLIT selects the kernel family: 0 = one warp per tile (decode_fast.cuh), 1 = state-split (decode_split.cuh)."""
+    monkeypatch.setenv("FSMC_SPLIT", str(request.param))
+    return request.param
+
+
+def test_fast_kernel_per_site_outputs_69_states(synthetic69, split):
     """Production kernel (FMA, rescaling every 4th site, bulk-copy ring): per-site posterior mean, IBD probability and MAP
     within the north-star tolerance of the oracle; ragged windows and a partially filled tile included."""
     from fastsmc_b200 import _native as N
@@ -182,14 +189,14 @@ def test_fast_kernel_per_site_outputs_69_states(synthetic69):
         nb = (len(a) + 31) // 32
         tiles = ctx.make_tiles(a, b, windows=[[frm, to]] * nb, sites=o.sites)
         r = ctx.decode(tiles, N.SITE_MEAN | N.SITE_MAP | N.SITE_IBD)
-        assert r.stats.statesKernel == 69
+        assert r.stats.statesKernel == 69 and r.stats.tileWarps == (2 if split else 1)
         rows = tiles["rows"]
         np.testing.assert_allclose(r.site_mean[rows, :to - frm], mean, rtol=REL_TOL)
         np.testing.assert_allclose(r.site_ibd[rows, :to - frm], ibd, rtol=REL_TOL, atol=1e-12)
         assert (r.site_map[rows, :to - frm] != mp).mean() < 2e-3
 
 
-def test_fast_kernel_segments_69_states(synthetic69):
+def test_fast_kernel_segments_69_states(synthetic69, split):
     """Whole all-pairs job slice through the production kernel vs the oracle: same segments (a boundary may move only
     where the IBD probability is within tolerance of a threshold), sums and age estimates within 1e-4."""
     from fastsmc_b200 import _native as N
@@ -209,7 +216,7 @@ def test_fast_kernel_segments_69_states(synthetic69):
     tiles = ctx.make_tiles(np.array(a), np.array(b), sites=o.sites)
     r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE, segment_capacity=1 << 20)
     seg = r.segments
-    assert r.stats.statesKernel == 69
+    assert r.stats.statesKernel == 69 and r.stats.tileWarps == (2 if split else 1)
     want = {(int(i[0]) * 32 + int(i[1]), int(i[4]), int(i[5])): f for i, f in zip(ints, floats)}
     got = {(int(s["pair"]), int(s["posStart"]), int(s["posEnd"])): s for s in seg}
     common = set(want) & set(got)
@@ -222,7 +229,7 @@ def test_fast_kernel_segments_69_states(synthetic69):
     assert (g[:, 2] != w[:, 2]).mean() < 5e-3
 
 
-def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69):
+def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69, split):
     """FastSMC's default flags (age estimates conditional on TMRCA < time): the kernel that keeps only the states below
     the threshold and carries the normaliser by the scale-factor recurrence (decodeNarrowKernel) gives the oracle's
     segments and per-site IBD probabilities within 1e-4, over a 3 000-site window (750 rescalings)."""
@@ -242,7 +249,7 @@ def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69):
     mean, mp, ibd = o.decode_summary(a, b, 0, o.sites, mean=False, map_=False)
     tiles = ctx.make_tiles(a, b, windows=[[0, o.sites]] * 3, sites=o.sites)
     r = ctx.decode(tiles, N.SITE_IBD)
-    assert r.stats.narrowKernel == 1
+    assert r.stats.narrowKernel == 1 and r.stats.tileWarps == (2 if split else 1)
     np.testing.assert_allclose(r.site_ibd[tiles["rows"]], ibd, rtol=REL_TOL, atol=1e-12)
     # segments with conditional age estimates: narrow vs the full-beta kernel (same arithmetic otherwise)
     rn = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE)
@@ -255,3 +262,57 @@ def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69):
     for f in ("prob", "postMean"):
         np.testing.assert_allclose([gn[k][f] for k in common], [gw[k][f] for k in common], rtol=REL_TOL)
     assert np.mean([gn[k]["mapState"] != gw[k]["mapState"] for k in common]) < 5e-3
+
+
+# ---- 159 states (FASTSMC_EXAMPLE table): the state-split kernels are the production path (4 warps per tile) ---------
+
+
+def test_split_kernels_159_states_default_flags(oracle_mod):
+    """FastSMC's default flags on the example data (age estimates conditional on TMRCA < time): the narrow state-split
+    kernel vs the oracle (per-site IBD probability within 1e-4, same segments) and vs the wide state-split kernel."""
+    from fastsmc_b200 import _native as N
+    params = dict(REGRESSION_PARAMS, noConditionalAgeEstimates=False)
+    o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test159n", hashing=True, **params)
+    assert o.age_threshold == o.state_threshold
+    n = o.run("/tmp/fsmc_test159n_oracle.ibd.gz")
+    ints, floats = o.segments()
+    batches = o.batches()
+    cands = o.candidates()
+    ctx = context_from_oracle(o, oracle_mod)
+    tiles = ctx.make_tiles(cands[:, 0], cands[:, 1], windows=batches[:, 3:5], scan=batches[:, 1:3], sites=o.sites)
+    for extra, narrow in ((0, 1), (N.WIDE_KERNEL, 0)):
+        r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE | extra)
+        assert r.stats.narrowKernel == narrow and r.stats.tileWarps == 4 and r.stats.statesKernel == 159
+        seg = r.segments
+        assert len(seg) == n
+        assert np.array_equal(seg["pair"], ints[:, 0] * 32 + ints[:, 1])
+        assert np.array_equal(seg["posStart"], ints[:, 4])
+        assert np.array_equal(seg["posEnd"], ints[:, 5])
+        np.testing.assert_allclose(seg["prob"], floats[:, 0], rtol=REL_TOL)
+        np.testing.assert_allclose(seg["postMean"], floats[:, 1], rtol=REL_TOL)
+        assert (seg["mapState"] != ints[:, 6]).mean() < 5e-3
+    # per-site IBD probability over ragged windows, a partially filled tile and a single-site window
+    rng = np.random.default_rng(3)
+    a, b = _pairs(rng, 45, o.num_haps)
+    for frm, to in ((0, o.sites), (311, 1999), (6759, 6760), (5, 7)):
+        _, _, ibd = o.decode_summary(a, b, frm, to, mean=False, map_=False)
+        t2 = ctx.make_tiles(a, b, windows=[[frm, to]] * 2, sites=o.sites)
+        r = ctx.decode(t2, N.SITE_IBD)
+        assert r.stats.narrowKernel == 1 and r.stats.tileWarps == 4
+        np.testing.assert_allclose(r.site_ibd[t2["rows"], :to - frm], ibd, rtol=REL_TOL, atol=1e-12)
+
+
+def test_one_warp_kernels_still_selectable_159(example):
+    """FSMC_ONE_WARP_KERNEL keeps the register/shared-memory kernel of decode_kernels.cuh reachable (A/B checks)."""
+    from fastsmc_b200 import _native as N
+    o, ctx = example
+    rng = np.random.default_rng(4)
+    a, b = _pairs(rng, 32, o.num_haps)
+    mean, mp, ibd = o.decode_summary(a, b, 100, 600)
+    tiles = ctx.make_tiles(a, b, windows=[[100, 600]], sites=o.sites)
+    r1 = ctx.decode(tiles, N.SITE_MEAN | N.SITE_IBD | N.ONE_WARP_KERNEL)
+    r4 = ctx.decode(tiles, N.SITE_MEAN | N.SITE_IBD)
+    assert r1.stats.tileWarps == 1 and r4.stats.tileWarps == 4
+    for r in (r1, r4):
+        np.testing.assert_allclose(r.site_mean[tiles["rows"], :500], mean, rtol=REL_TOL)
+        np.testing.assert_allclose(r.site_ibd[tiles["rows"], :500], ibd, rtol=REL_TOL, atol=1e-12)

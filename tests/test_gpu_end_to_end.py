@@ -108,7 +108,7 @@ def test_binary_output_round_trip(asmc, tmp_path):
     out = []
     while r.moreLinesInFile():
         out.append(r.getNextLine().toString())
-    assert len(out) == len(text)
+    assert len(out) == len(text), (len(out), len(text))
     assert [l.split("\t")[:9] for l in out] == [l.split("\t")[:9] for l in text]
     a = np.array([[float(x) for x in l.split("\t")[9:]] for l in out])
     b = np.array([[float(x) for x in l.split("\t")[9:]] for l in text])

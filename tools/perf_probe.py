@@ -45,6 +45,8 @@ if tiles is None:
                  tileScanTo=e, rows=np.arange(n))
 for flags, name in ((N.CALL_SEGMENTS | N.SEG_AGE, "segments+age"), (N.CALL_SEGMENTS, "segments"),
                     (N.CALL_SEGMENTS | N.SEG_AGE | N.EXACT, "segments+age exact")):
+    if (flags & N.EXACT) and os.environ.get("PROBE_SKIP_EXACT", "0") == "1":
+        continue
     flags |= flags_extra
     plan = ctx.plan(tiles, flags, segment_capacity=1 << 22)
     for it in range(3):
@@ -53,5 +55,5 @@ for flags, name in ((N.CALL_SEGMENTS | N.SEG_AGE, "segments+age"), (N.CALL_SEGME
         ps = r.stats.pairSites
         print(f"{name}: kernel {r.stats.kernelMs:.2f} ms  {ps / r.stats.kernelMs / 1e6:.3f} G pair-sites/s  "
               f"segs {r.stats.numSegments} scratch {r.stats.scratchBytes / 2**30:.1f} GiB  S_kernel {r.stats.statesKernel} "
-              f"beta GB/s {ps * o.states * 8 / r.stats.kernelMs / 1e6:.0f} narrow {r.stats.narrowKernel}")
+              f"beta GB/s {ps * o.states * 8 / r.stats.kernelMs / 1e6:.0f} narrow {r.stats.narrowKernel} tileWarps {r.stats.tileWarps}")
     plan.close()
