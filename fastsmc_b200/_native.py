@@ -23,6 +23,9 @@ EXACT = 0x20
 GENERIC_KERNEL = 0x40
 WIDE_KERNEL = 0x80
 ONE_WARP_KERNEL = 0x100
+SITE_POSTERIOR = 0x200
+SUM_POSTERIOR = 0x400
+SUM_BY_GENOTYPE = 0x800
 
 E_OVERFLOW = -4
 
@@ -53,6 +56,7 @@ class Request(C.Structure):
         ("flags", C.c_uint32),
         ("segments", C.c_void_p), ("segmentCapacity", C.c_int64),
         ("siteMean", C.c_void_p), ("siteMap", C.c_void_p), ("siteIbd", C.c_void_p), ("siteStride", C.c_int64),
+        ("sitePosterior", C.c_void_p), ("sumPosterior", C.c_void_p),
     ]
 
 
@@ -127,12 +131,14 @@ def pack_haplotypes(haps):
 
 
 class DecodeResult:
-    def __init__(self, segments, site_mean, site_map, site_ibd, stats):
+    def __init__(self, segments, site_mean, site_map, site_ibd, stats, site_posterior=None, sum_posterior=None):
         self.segments = segments
         self.site_mean = site_mean
         self.site_map = site_map
         self.site_ibd = site_ibd
         self.stats = stats
+        self.site_posterior = site_posterior  # [pairs][states][siteStride]
+        self.sum_posterior = sum_posterior    # [planes][states][sites]
 
 
 class Context:
@@ -223,33 +229,41 @@ class Context:
                     tilePairs=np.array(tn, np.int32), tileFrom=np.array(tf, np.int32), tileTo=np.array(tt, np.int32),
                     tileScanFrom=np.array(sf, np.int32), tileScanTo=np.array(stt, np.int32), rows=rows)
 
-    def _request(self, tiles, flags, segment_capacity, site_stride):
+    def _request(self, tiles, flags, segment_capacity, site_stride, segment_prefill=None):
         T = len(tiles["tilePairs"])
         out = {}
         seg = np.zeros(max(segment_capacity, 1), SEGMENT_DTYPE) if flags & CALL_SEGMENTS else None
+        if seg is not None and segment_prefill is not None:
+            # previous contents of the caller's record buffer (the library must not depend on them)
+            n = min(len(seg), len(segment_prefill))
+            seg[:n] = segment_prefill[:n]
         stride = 0
-        if flags & (SITE_MEAN | SITE_MAP | SITE_IBD):
+        if flags & (SITE_MEAN | SITE_MAP | SITE_IBD | SITE_POSTERIOR):
             stride = site_stride or int((tiles["tileTo"] - tiles["tileFrom"]).max()) if T else 0
         mean = np.zeros((T * TILE, stride), np.float32) if flags & SITE_MEAN else None
         smap = np.zeros((T * TILE, stride), np.int32) if flags & SITE_MAP else None
         ibd = np.zeros((T * TILE, stride), np.float32) if flags & SITE_IBD else None
+        post = np.zeros((T * TILE, self.states, stride), np.float32) if flags & SITE_POSTERIOR else None
+        psum = (np.zeros((3 if flags & SUM_BY_GENOTYPE else 1, self.states, self.sites), np.float32)
+                if flags & SUM_POSTERIOR else None)
         req = Request(T, _p(tiles["hapA"]), _p(tiles["hapB"]), _p(tiles["tilePairs"]), _p(tiles["tileFrom"]),
                       _p(tiles["tileTo"]), _p(tiles["tileScanFrom"]), _p(tiles["tileScanTo"]), flags,
-                      _p(seg), segment_capacity if seg is not None else 0, _p(mean), _p(smap), _p(ibd), stride)
-        out.update(seg=seg, mean=mean, smap=smap, ibd=ibd)
+                      _p(seg), segment_capacity if seg is not None else 0, _p(mean), _p(smap), _p(ibd), stride,
+                      _p(post), _p(psum))
+        out.update(seg=seg, mean=mean, smap=smap, ibd=ibd, post=post, psum=psum)
         return req, out
 
-    def decode(self, tiles, flags, segment_capacity=1 << 20, site_stride=0):
+    def decode(self, tiles, flags, segment_capacity=1 << 20, site_stride=0, segment_prefill=None):
         """One-shot fsmc_decode with host buffers.  Grows the segment buffer and retries on overflow."""
         while True:
-            req, out = self._request(tiles, flags, segment_capacity, site_stride)
+            req, out = self._request(tiles, flags, segment_capacity, site_stride, segment_prefill)
             stats = Stats()
             rc = _check(lib().fsmc_decode(self._h, C.byref(req), C.byref(stats)), allow=(E_OVERFLOW,))
             if rc == E_OVERFLOW:
                 segment_capacity = int(stats.numSegments) + 1024
                 continue
             seg = out["seg"][:stats.numSegments] if out["seg"] is not None else None
-            return DecodeResult(seg, out["mean"], out["smap"], out["ibd"], stats)
+            return DecodeResult(seg, out["mean"], out["smap"], out["ibd"], stats, out["post"], out["psum"])
 
     # ---- split phase (device-resident inputs)
     def plan(self, tiles, flags, segment_capacity=1 << 20, site_stride=0):
@@ -271,7 +285,7 @@ class Plan:
         _check(lib().fsmc_plan_collect(self.ctx._h, self._h, C.byref(self._req), C.byref(stats)))
         o = self._out
         seg = o["seg"][:stats.numSegments] if o["seg"] is not None else None
-        return DecodeResult(seg, o["mean"], o["smap"], o["ibd"], stats)
+        return DecodeResult(seg, o["mean"], o["smap"], o["ibd"], stats, o["post"], o["psum"])
 
     def close(self):
         if self._h:

@@ -100,6 +100,16 @@ template <class T> struct PinnedBuf {
 
 struct fsmc_plan;
 
+struct SeedKey {
+  int32_t gap;
+  float minLengthCm;
+  const void* geneticPositions;
+  const void* globalHapId;
+  uint32_t window[4];
+  int32_t lastJob, aboveDiag;
+  uint32_t flags;
+};
+
 struct fsmc_ctx {
   int device = 0;
   cudaStream_t ownStream = nullptr;
@@ -117,13 +127,16 @@ struct fsmc_ctx {
   DevBuf<uint64_t> seedKeysT;
   DevBuf<uint32_t> seedOwner, seedSlotCount, seedSlotGroup, seedSlotOf, seedRankOf, seedMembers, seedGroupSize,
       seedGroupMemberBase, seedGlobalId;
-  DevBuf<unsigned long long> seedGroupPairBase, seedCounters;
+  DevBuf<unsigned long long> seedGroupPairBase, seedCounters, seedWordCounters, seedChunkBase;
   DevBuf<float> seedGenPos;
   DevBuf<fsmc_match> seedOut;
+  bool seedCacheValid = false;  // seedOut holds every interval of the last fsmc_seed call (which overflowed the caller)
+  SeedKey seedCacheKey{};
+  fsmc_seed_stats seedCacheStats{};
   cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
   // host staging of segment records and the per-pair counters of their counting sort (fsmc_plan_collect)
   PinnedBuf<fsmc_segment> segStage;
-  std::vector<uint32_t> pairOffset;
+  std::vector<uint32_t> pairOffset, pairFirst;
   // a destroyed plan is parked here so that the next fsmc_plan_create reuses its device buffers (fsmc_decode makes
   // one plan per call; cudaMalloc/cudaFree per call would serialise the device)
   fsmc_plan* sparePlan = nullptr;
@@ -141,7 +154,7 @@ struct fsmc_plan {
   std::vector<int> hostOrder;  // source of the asynchronous copy into `order`
   DevBuf<fsmc_segment> segments;
   DevBuf<unsigned long long> counters;  // [0] segment count, [1] tile queue head
-  DevBuf<float> siteMean, siteIbd;
+  DevBuf<float> siteMean, siteIbd, sitePosterior, sumPosterior;
   DevBuf<int> siteMap;
   // launch geometry
   int statesKernel = 0;
@@ -218,7 +231,8 @@ int splitPreference()
 FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
 {
   const int S = m.S;
-  if ((flags & (FSMC_EXACT | FSMC_GENERIC_KERNEL)) || S > fsmc::kMaxParamStates) {
+  // full posteriors and their sums are produced by decodeTilesKernel only
+  if ((flags & (FSMC_EXACT | FSMC_GENERIC_KERNEL | FSMC_SITE_POSTERIOR | FSMC_SUM_POSTERIOR)) || S > fsmc::kMaxParamStates) {
     return {};
   }
   const bool acc = (flags & FSMC_SEG_AGE) && (flags & FSMC_CALL_SEGMENTS);
@@ -270,6 +284,11 @@ size_t fastSmemBytes(const FastChoice& fc, const int S)
   return warps * (kFastDepth * (static_cast<size_t>(fc.Spad) * 32 * 4 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4) +
                   0 * static_cast<size_t>(S)) +
          warps * 2 * kFastDepth * sizeof(uint64_t);
+}
+
+size_t sumPosteriorCount(const DeviceModel& m, const unsigned flags)
+{
+  return static_cast<size_t>((flags & FSMC_SUM_BY_GENOTYPE) ? 3 : 1) * static_cast<size_t>(m.S) * static_cast<size_t>(m.L);
 }
 
 size_t smemPerWarp(const DeviceModel& m, const int mode, const unsigned flags)
@@ -467,6 +486,7 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, const int64_t numHa
   ctx->numHaps = numHaps;
   ctx->sites = sites;
   ctx->hasHaps = true;
+  ctx->seedCacheValid = false;
   return FSMC_OK;
 }
 
@@ -485,7 +505,10 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   }
   const unsigned flags = req->flags;
   const bool seg = flags & FSMC_CALL_SEGMENTS;
-  const bool siteOut = flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP | FSMC_SITE_IBD);
+  const bool siteOut = flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP | FSMC_SITE_IBD | FSMC_SITE_POSTERIOR);
+  if ((flags & FSMC_SUM_BY_GENOTYPE) && !(flags & FSMC_SUM_POSTERIOR)) {
+    return fail(FSMC_E_INVALID, "fsmc_plan_create: FSMC_SUM_BY_GENOTYPE needs FSMC_SUM_POSTERIOR");
+  }
   if (T > 0 && (!req->hapA || !req->hapB || !req->tilePairs || !req->tileFrom || !req->tileTo ||
                 (seg && (!req->tileScanFrom || !req->tileScanTo)))) {
     return fail(FSMC_E_INVALID, "fsmc_plan_create: NULL input array");
@@ -584,6 +607,12 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   }
   if (flags & FSMC_SITE_IBD) {
     FSMC_CUDA(plan->siteIbd.ensure(nSite));
+  }
+  if (flags & FSMC_SITE_POSTERIOR) {
+    FSMC_CUDA(plan->sitePosterior.ensure(nSite * static_cast<size_t>(ctx->model.S)));
+  }
+  if (flags & FSMC_SUM_POSTERIOR) {
+    FSMC_CUDA(plan->sumPosterior.ensure(sumPosteriorCount(ctx->model, flags)));
   }
   plan->launched = false;
   plan->launches = 0;
@@ -684,6 +713,11 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
     a.siteMean = plan->siteMean.p;
     a.siteMap = plan->siteMap.p;
     a.siteIbd = plan->siteIbd.p;
+    a.sitePosterior = plan->sitePosterior.p;
+    a.sumPosterior = plan->sumPosterior.p;
+    if (plan->flags & FSMC_SUM_POSTERIOR) {
+      FSMC_CUDA(cudaMemsetAsync(plan->sumPosterior.p, 0, sumPosteriorCount(m, plan->flags) * sizeof(float), st));
+    }
     a.siteStride = plan->siteStride;
     a.scratch = ctx->scratch.p;
     a.scratchPerWarp = plan->scratchPerWarp;
@@ -757,6 +791,20 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
     }
     FSMC_CUDA(cudaMemcpyAsync(out->siteIbd, plan->siteIbd.p, nSite * sizeof(float), cudaMemcpyDeviceToHost, st));
   }
+  if ((flags & FSMC_SITE_POSTERIOR) && nSite) {
+    if (!out->sitePosterior) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_collect: sitePosterior is NULL");
+    }
+    FSMC_CUDA(cudaMemcpyAsync(out->sitePosterior, plan->sitePosterior.p,
+                              nSite * static_cast<size_t>(ctx->model.S) * sizeof(float), cudaMemcpyDeviceToHost, st));
+  }
+  if (flags & FSMC_SUM_POSTERIOR) {
+    if (!out->sumPosterior) {
+      return fail(FSMC_E_INVALID, "fsmc_plan_collect: sumPosterior is NULL");
+    }
+    FSMC_CUDA(cudaMemcpyAsync(out->sumPosterior, plan->sumPosterior.p, sumPosteriorCount(ctx->model, flags) * sizeof(float),
+                              cudaMemcpyDeviceToHost, st));
+  }
   FSMC_CUDA(cudaEventRecord(ctx->ev[3], st));
   FSMC_CUDA(cudaStreamSynchronize(st));
   if (stored > 0) {
@@ -776,10 +824,17 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
     for (size_t q = 0; q < nPairs; ++q) {
       off[q + 1] += off[q];
     }
+    // After the scan off[q] is the first slot of pair q; it then advances as the pair's records arrive.  The guard only
+    // looks at slots of the SAME pair that are already filled: the slot before them belongs to another pair and may
+    // still hold whatever the caller's buffer contained before the call.
+    std::vector<uint32_t>& first = ctx->pairFirst;
+    first.assign(off.begin(), off.end() - 1);
     for (long long i = 0; i < stored; ++i) {
-      fsmc_segment* dst = out->segments + off[in[i].pair]++;
+      const uint32_t q = in[i].pair;
+      fsmc_segment* const lo = out->segments + first[q];
+      fsmc_segment* dst = out->segments + off[q]++;
       *dst = in[i];
-      while (dst > out->segments && dst[-1].pair == dst->pair && dst[-1].posStart > dst->posStart) {
+      while (dst > lo && dst[-1].posStart > dst->posStart) {
         std::swap(dst[-1], dst[0]);
         --dst;
       }
@@ -840,25 +895,60 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   const uint32_t H = static_cast<uint32_t>(ctx->numHaps);
   const int L = static_cast<int>(ctx->sites);
   const int W = L / 64;  // a trailing partial word is never hashed
+  // A call that overflowed the caller's buffer leaves its intervals on the device; the retry with a larger buffer and
+  // the same parameters only copies them out.
+  SeedKey key;
+  std::memset(&key, 0, sizeof key);
+  key.gap = sp->gap;
+  key.minLengthCm = sp->minLengthCm;
+  key.geneticPositions = sp->geneticPositions;
+  key.globalHapId = sp->globalHapId;
+  key.window[0] = sp->loI;
+  key.window[1] = sp->hiI;
+  key.window[2] = sp->loJ;
+  key.window[3] = sp->hiJ;
+  key.lastJob = sp->lastJob;
+  key.aboveDiag = sp->aboveDiag;
+  key.flags = sp->flags;
+  const bool cacheHit = ctx->seedCacheValid && std::memcmp(&key, &ctx->seedCacheKey, sizeof key) == 0 &&
+                        capacity >= ctx->seedCacheStats.numMatches;
+  if (!cacheHit) {
+  ctx->seedCacheValid = false;
   uint32_t C = 64;
   while (C < 2u * H) {
     C <<= 1;
   }
   const size_t maxGroups = H / 2 + 2;
+  // Words are independent, so a launch handles a batch of them (blockIdx.y = word in the batch), each with its own
+  // slice of the scratch tables: at small sample counts the per-word kernels are a few microseconds of work and the
+  // pass would otherwise be bound by launch latency (5 launches per word).  The batch is as large as 2 GiB of tables
+  // allow, up to 64 words.
+  const size_t perWordBytes = static_cast<size_t>(C) * 12 + static_cast<size_t>(H) * 12 + maxGroups * 16 + 40;
+  const int WB = static_cast<int>(std::max<size_t>(1, std::min<size_t>({64, static_cast<size_t>(std::max(W, 1)),
+                                                                       (size_t{2} << 30) / perWordBytes})));
   FSMC_CUDA(ctx->seedKeysT.ensure(static_cast<size_t>(std::max(W, 1)) * H));
-  FSMC_CUDA(ctx->seedOwner.ensure(C));
-  FSMC_CUDA(ctx->seedSlotCount.ensure(C));
-  FSMC_CUDA(ctx->seedSlotGroup.ensure(C));
-  FSMC_CUDA(ctx->seedSlotOf.ensure(H));
-  FSMC_CUDA(ctx->seedRankOf.ensure(H));
-  FSMC_CUDA(ctx->seedMembers.ensure(H));
-  FSMC_CUDA(ctx->seedGroupSize.ensure(maxGroups));
-  FSMC_CUDA(ctx->seedGroupMemberBase.ensure(maxGroups));
-  FSMC_CUDA(ctx->seedGroupPairBase.ensure(maxGroups + 1));
+  FSMC_CUDA(ctx->seedOwner.ensure(static_cast<size_t>(WB) * C));
+  FSMC_CUDA(ctx->seedSlotCount.ensure(static_cast<size_t>(WB) * C));
+  FSMC_CUDA(ctx->seedSlotGroup.ensure(static_cast<size_t>(WB) * C));
+  FSMC_CUDA(ctx->seedSlotOf.ensure(static_cast<size_t>(WB) * H));
+  FSMC_CUDA(ctx->seedRankOf.ensure(static_cast<size_t>(WB) * H));
+  FSMC_CUDA(ctx->seedMembers.ensure(static_cast<size_t>(WB) * H));
+  FSMC_CUDA(ctx->seedGroupSize.ensure(static_cast<size_t>(WB) * maxGroups));
+  FSMC_CUDA(ctx->seedGroupMemberBase.ensure(static_cast<size_t>(WB) * maxGroups));
+  FSMC_CUDA(ctx->seedGroupPairBase.ensure(static_cast<size_t>(WB) * (maxGroups + 1)));
+  FSMC_CUDA(ctx->seedWordCounters.ensure(static_cast<size_t>(WB) * 4));
+  FSMC_CUDA(ctx->seedChunkBase.ensure(static_cast<size_t>(WB) + 2));
   FSMC_CUDA(ctx->seedCounters.ensure(8));
   FSMC_CUDA(ctx->seedGenPos.ensure(L));
   FSMC_CUDA(ctx->seedGlobalId.ensure(H));
-  FSMC_CUDA(ctx->seedOut.ensure(static_cast<size_t>(capacity)));
+  // device-side interval buffer: at least 16 Mi intervals (256 MiB) whatever the caller's capacity, so that an
+  // under-sized first call does not have to be recomputed
+  size_t freeB = 0, totalB = 0;
+  FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+  const long long devCap = std::max<long long>(
+      capacity, std::min<long long>(1ll << 24, static_cast<long long>((freeB + ctx->seedOut.n * sizeof(fsmc_match)) / 4 /
+                                                                       sizeof(fsmc_match))));
+  FSMC_CUDA(ctx->seedOut.ensure(static_cast<size_t>(devCap)));
   FSMC_CUDA(cudaMemcpyAsync(ctx->seedGenPos.p, sp->geneticPositions, sizeof(float) * L, cudaMemcpyHostToDevice, st));
   FSMC_CUDA(cudaMemcpyAsync(ctx->seedGlobalId.p, sp->globalHapId, sizeof(uint32_t) * H, cudaMemcpyHostToDevice, st));
   FSMC_CUDA(cudaMemsetAsync(ctx->seedCounters.p, 0, 8 * sizeof(unsigned long long), st));
@@ -891,9 +981,12 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   a.groupMemberBase = ctx->seedGroupMemberBase.p;
   a.groupPairBase = ctx->seedGroupPairBase.p;
   a.members = ctx->seedMembers.p;
+  a.maxGroups = static_cast<uint32_t>(maxGroups);
+  a.wordCounters = ctx->seedWordCounters.p;
+  a.batchChunkBase = ctx->seedChunkBase.p;
   a.counters = ctx->seedCounters.p;
   a.out = ctx->seedOut.p;
-  a.capacity = capacity;
+  a.capacity = devCap;
 
   int launches = 0;
   FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
@@ -902,18 +995,24 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
     const dim3 tb(32, 8), tg((H + 31) / 32, (W + 31) / 32);
     fsmc::transposeWordsKernel<<<tg, tb, 0, st>>>(a.haps, a.wordsPerHap, H, W, ctx->seedKeysT.p);
     ++launches;
-    const int hapBlocks = static_cast<int>(std::min<long long>((H + 255ll) / 256, sms * 8ll));
-    const int slotBlocks = static_cast<int>(std::min<long long>((C + 255ll) / 256, sms * 8ll));
-    for (int w = 0; w < W; ++w) {
-      FSMC_CUDA(cudaMemsetAsync(a.owner, 0, sizeof(uint32_t) * C, st));
-      FSMC_CUDA(cudaMemsetAsync(a.slotCount, 0, sizeof(uint32_t) * C, st));
-      FSMC_CUDA(cudaMemsetAsync(a.counters, 0, sizeof(unsigned long long), st));  // numGroups
-      fsmc::groupInsertKernel<<<hapBlocks, 256, 0, st>>>(a, w);
-      fsmc::groupCompactKernel<<<slotBlocks, 256, 0, st>>>(a);
-      fsmc::groupScanKernel<<<1, 1024, 0, st>>>(a);
-      fsmc::groupScatterKernel<<<hapBlocks, 256, 0, st>>>(a);
-      fsmc::pairExtendKernel<<<sms * 8, 256, 0, st>>>(a, w);
-      launches += 5;
+    for (int w0 = 0; w0 < W; w0 += WB) {
+      const unsigned nw = static_cast<unsigned>(std::min(WB, W - w0));
+      // grid.x: enough CTAs per word to cover it, but no more than ~8 CTAs per SM over the whole batch
+      const long long perWordCap = std::max<long long>(1, sms * 8ll / nw);
+      const unsigned hapBlocks = static_cast<unsigned>(std::min<long long>((H + 255ll) / 256, perWordCap));
+      const unsigned slotBlocks = static_cast<unsigned>(std::min<long long>((C + 255ll) / 256, perWordCap));
+      a.wordBase = w0;
+      a.wordsInBatch = static_cast<int>(nw);
+      FSMC_CUDA(cudaMemsetAsync(a.owner, 0, sizeof(uint32_t) * C * nw, st));
+      FSMC_CUDA(cudaMemsetAsync(a.slotCount, 0, sizeof(uint32_t) * C * nw, st));
+      FSMC_CUDA(cudaMemsetAsync(a.wordCounters, 0, sizeof(unsigned long long) * 4 * nw, st));
+      fsmc::groupInsertKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
+      fsmc::groupCompactKernel<<<dim3(slotBlocks, nw), 256, 0, st>>>(a);
+      fsmc::groupScanKernel<<<nw, 1024, 0, st>>>(a);
+      fsmc::groupScatterKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
+      fsmc::batchChunksKernel<<<1, 32, 0, st>>>(a);
+      fsmc::pairExtendKernel<<<sms * 8, fsmc::kPairBlockThreads, 0, st>>>(a);
+      launches += 6;
     }
     FSMC_CUDA(cudaGetLastError());
   }
@@ -921,8 +1020,32 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   unsigned long long counters[8] = {0};
   FSMC_CUDA(cudaMemcpyAsync(counters, ctx->seedCounters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
   FSMC_CUDA(cudaStreamSynchronize(st));
-  const long long found = static_cast<long long>(counters[3]);
-  const long long stored = std::min<long long>(found, capacity);
+  {
+    fsmc_seed_stats& cs = ctx->seedCacheStats;
+    cs.numMatches = static_cast<int64_t>(counters[3]);
+    cs.pairVisits = static_cast<int64_t>(counters[4]);
+    cs.numStarts = static_cast<int64_t>(counters[5]);
+    cs.numWords = W;
+    cs.kernelLaunches = launches;
+    cs.kernelMs = 0.f;
+    cudaEventElapsedTime(&cs.kernelMs, ctx->ev[1], ctx->ev[2]);
+    // every packed word read and written once by the transpose, read once by the grouping pass; slot table cleared
+    // and probed; three per-haplotype bookkeeping words; 16 bytes per emitted interval
+    cs.bytesRead = static_cast<int64_t>(W) * (static_cast<int64_t>(H) * (8 + 8 + 8 + 12) + static_cast<int64_t>(C) * 12) +
+                   16 * cs.numMatches;
+    ctx->seedCacheKey = key;
+    ctx->seedCacheValid = cs.numMatches <= devCap;  // everything found is on the device
+  }
+  }  // !cacheHit
+  const long long found = static_cast<long long>(ctx->seedCacheStats.numMatches);
+  if (stats) {
+    *stats = ctx->seedCacheStats;
+  }
+  if (found > capacity) {
+    return fail(FSMC_E_OVERFLOW, "fsmc_seed: %lld intervals found, capacity %lld", found, static_cast<long long>(capacity));
+  }
+  ctx->seedCacheValid = false;  // consumed by this call
+  const long long stored = found;
   if (stored > 0) {
     // canonical candidate order (endWord, hapA, hapB): counting sort by end word from a staging copy into the
     // caller's buffer, then every end-word bucket is sorted by pair on its own host thread
@@ -962,22 +1085,6 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
     for (auto& th : pool) {
       th.join();
     }
-  }
-  if (stats) {
-    stats->numMatches = found;
-    stats->pairVisits = static_cast<int64_t>(counters[4]);
-    stats->numStarts = static_cast<int64_t>(counters[5]);
-    stats->numWords = W;
-    stats->kernelLaunches = launches;
-    stats->kernelMs = 0.f;
-    cudaEventElapsedTime(&stats->kernelMs, ctx->ev[1], ctx->ev[2]);
-    // every packed word read and written once by the transpose, read once by the grouping pass; slot table cleared
-    // and probed; three per-haplotype bookkeeping words; 16 bytes per emitted interval
-    stats->bytesRead = static_cast<int64_t>(W) * (static_cast<int64_t>(H) * (8 + 8 + 8 + 12) + static_cast<int64_t>(C) * 12) +
-                       16 * found;
-  }
-  if (found > capacity) {
-    return fail(FSMC_E_OVERFLOW, "fsmc_seed: %lld intervals found, capacity %lld", found, static_cast<long long>(capacity));
   }
   return FSMC_OK;
 }

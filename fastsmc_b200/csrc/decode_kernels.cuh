@@ -64,6 +64,8 @@ struct DecodeArgs {
   int* siteMap;
   float* siteIbd;
   long long siteStride;
+  float* sitePosterior;        // [pair][S][siteStride]
+  float* sumPosterior;         // [planes][S][L]
   float* scratch;              // beta slabs
   long long scratchPerWarp;    // floats per warp slab
   float* accScratch;           // fast kernel: per-warp [S][32] per-state segment sums
@@ -334,6 +336,7 @@ __device__ __forceinline__ void sweepForward(const DeviceModel& m, const DecodeA
   const bool wantAge = (flags & FSMC_SEG_AGE) && wantSeg;
   const int sT = m.stateThreshold;
   const int nAcc = m.ageThreshold;
+  const bool lane0 = (threadIdx.x & 31) == 0;
   CallerState cs;
 
   for (int p = 0; p < len; ++p) {
@@ -443,6 +446,33 @@ __device__ __forceinline__ void sweepForward(const DeviceModel& m, const DecodeA
         }
         if (flags & FSMC_SITE_MAP) {
           args.siteMap[static_cast<size_t>(pair) * args.siteStride + p] = arg;
+        }
+      }
+    }
+
+    // ---- full posteriors and their sum over pairs (ref HMM.cpp:1372-1389, 1044-1085) ----------
+    if (flags & (FSMC_SITE_POSTERIOR | FSMC_SUM_POSTERIOR)) {
+      float* postRow = args.sitePosterior + static_cast<size_t>(pair) * S * args.siteStride + p;
+      // plane of the sum this lane's pair contributes to: its genotype class at the site, or the only plane
+      const int plane = (flags & FSMC_SUM_BY_GENOTYPE) ? bits.cls(site) : 0;
+      const int nPlanes = (flags & FSMC_SUM_BY_GENOTYPE) ? 3 : 1;
+#pragma unroll
+      for (int k = 0; k < S; ++k) {
+        const float post = __fmul_rn(c.get(k), r);
+        if ((flags & FSMC_SITE_POSTERIOR) && laneActive) {
+          postRow[static_cast<size_t>(k) * args.siteStride] = post;
+        }
+        if (flags & FSMC_SUM_POSTERIOR) {
+          for (int pl = 0; pl < nPlanes; ++pl) {
+            float v = (laneActive && plane == pl) ? post : 0.f;
+#pragma unroll
+            for (int d = 16; d > 0; d >>= 1) {
+              v += __shfl_xor_sync(kFull, v, d);
+            }
+            if (lane0 && v != 0.f) {
+              atomicAdd(args.sumPosterior + (static_cast<size_t>(pl) * S + k) * m.L + site, v);
+            }
+          }
         }
       }
     }

@@ -82,6 +82,15 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
   m_decodingReturnValues.sites = data.sites;
   m_decodingReturnValues.states = m_decodingQuant.states;
   m_decodingReturnValues.siteWasFlippedDuringFolding = data.siteWasFlippedDuringFolding;
+  // ref: HMM.cpp:271-279
+  if (decodingParams.doPosteriorSums) {
+    m_decodingReturnValues.sumOverPairs.resize(data.sites, m_decodingQuant.states);
+  }
+  if (decodingParams.doMajorMinorPosteriorSums) {
+    m_decodingReturnValues.sumOverPairs00.resize(data.sites, m_decodingQuant.states);
+    m_decodingReturnValues.sumOverPairs01.resize(data.sites, m_decodingQuant.states);
+    m_decodingReturnValues.sumOverPairs11.resize(data.sites, m_decodingQuant.states);
+  }
   // 8192 reference batches per kernel launch keep every SM busy; batch composition is unaffected because chunks
   // are cut at multiples of the batch size
   m_flushPairs = static_cast<size_t>(m_batchSize) * 8192;
@@ -341,9 +350,7 @@ void HMM::decodeAll(const int jobs, const int jobInd)
     }
     submit(2 * i, 2 * i + 1);
   }
-  if (decodingParams.FastSMC) {
-    finishDecoding();
-  }
+  finishDecoding();  // ref: HMM.cpp:359 (runLastBatch)
 }
 
 // ref: HMM.cpp:470-502
@@ -400,9 +407,11 @@ void HMM::decodeHapPair(const unsigned long i, const unsigned long j)
   m_pendingRow.push_back(m_decodePairsReturnStruct.getNumWritten() + m_pending.size());
   m_pending.push_back(Pending{static_cast<uint32_t>(i), static_cast<uint32_t>(j), 0u, static_cast<uint32_t>(data.sites)});
   // per-site outputs are pairs x sites floats: keep chunks small enough for host and device buffers
-  const size_t perSiteChunk =
-      std::max<size_t>(static_cast<size_t>(m_batchSize),
-                       (size_t{1} << 28) / std::max<size_t>(1, static_cast<size_t>(data.sites)) / m_batchSize * m_batchSize);
+  // (full posterior matrices are states times larger)
+  const size_t perPairFloats = std::max<size_t>(1, static_cast<size_t>(data.sites)) *
+                               (m_storePerPairPosterior ? static_cast<size_t>(m_decodingQuant.states) + 2 : 2);
+  const size_t perSiteChunk = std::max<size_t>(static_cast<size_t>(m_batchSize),
+                                               (size_t{1} << 29) / perPairFloats / m_batchSize * m_batchSize);
   if (!decodingParams.FastSMC && m_pending.size() >= perSiteChunk) {
     flushPending(false);
   }
@@ -455,6 +464,8 @@ void HMM::flushPending(const bool all)
   } else if (m_storePerPairPosteriorMean || m_storePerPairMAP || m_storePerPairPosterior || m_storeSumOfPosterior) {
     runPerSiteChunk(m_pending.data(), m_pendingRow.data(), n);
     m_pendingRow.erase(m_pendingRow.begin(), m_pendingRow.begin() + n);
+  } else if (decodingParams.doPosteriorSums || decodingParams.doMajorMinorPosteriorSums) {
+    runPosteriorSumChunk(m_pending.data(), n);
   }
   m_pending.erase(m_pending.begin(), m_pending.begin() + n);
 }
@@ -655,14 +666,10 @@ void HMM::formatSegments(const SegmentBlock& block, const size_t lo, const size_
 // Per-site posterior mean / MAP for ASMC::decodePairs (ref: HMM.cpp:1360-1458)
 void HMM::runPerSiteChunk(const Pending* pend, const unsigned long* rows, const size_t n)
 {
-  if (m_storePerPairPosterior || m_storeSumOfPosterior) {
-    throw std::runtime_error(
-        "per-pair posterior matrices / sum of posteriors are not produced by the B200 build (per-site posterior "
-        "means and MAPs are)");
-  }
   const TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), false, data.geneticPositions, data.sites);
   const size_t T = t.pairs.size();
   const int L = data.sites;
+  const int S = static_cast<int>(m_decodingQuant.states);
   fsmc_decode_request req{};
   req.numTiles = static_cast<int64_t>(T);
   req.hapA = t.hapA.data();
@@ -672,12 +679,22 @@ void HMM::runPerSiteChunk(const Pending* pend, const unsigned long* rows, const 
   req.tileTo = t.to.data();
   // the reference computes the MAP rows only under the posterior-mean flag (ref: HMM.cpp:1447-1449); both outputs
   // are produced here whenever either is stored
-  req.flags = FSMC_SITE_MEAN | FSMC_SITE_MAP | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
+  req.flags = FSMC_SITE_MEAN | FSMC_SITE_MAP | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u) |
+              (m_storePerPairPosterior ? FSMC_SITE_POSTERIOR : 0u) | (m_storeSumOfPosterior ? FSMC_SUM_POSTERIOR : 0u);
   std::vector<float> mean(T * FSMC_TILE * static_cast<size_t>(L));
   std::vector<int32_t> map(T * FSMC_TILE * static_cast<size_t>(L));
+  std::vector<float> post, postSum;
   req.siteMean = mean.data();
   req.siteMap = map.data();
   req.siteStride = L;
+  if (m_storePerPairPosterior) {
+    post.resize(T * FSMC_TILE * static_cast<size_t>(S) * static_cast<size_t>(L));
+    req.sitePosterior = post.data();
+  }
+  if (m_storeSumOfPosterior) {
+    postSum.resize(static_cast<size_t>(S) * static_cast<size_t>(L));
+    req.sumPosterior = postSum.data();
+  }
   fsmc_decode_stats st{};
   const double t0 = now();
   check(fsmc_decode(m_ctx, &req, &st), "fsmc_decode");
@@ -703,8 +720,83 @@ void HMM::runPerSiteChunk(const Pending* pend, const unsigned long* rows, const 
       if (m_storePerPairMAP) {
         std::memcpy(out.perPairMAPs.row(static_cast<long>(row)), &map[src], sizeof(int32_t) * L);
       }
+      if (m_storePerPairPosterior) {
+        // the reference stores posterior * expectedCoalTimes[k] (ref: HMM.cpp:1382-1386)
+        auto& dst = out.perPairPosteriors.at(row);
+        const float* srcPost = &post[(tile * FSMC_TILE + lane) * static_cast<size_t>(S) * L];
+        for (int k = 0; k < S; ++k) {
+          const float e = m_decodingQuant.expectedTimes[k];
+          float* d = dst.row(k);
+          for (int s2 = 0; s2 < L; ++s2) {
+            d[s2] = srcPost[static_cast<size_t>(k) * L + s2] * e;
+          }
+        }
+      }
       out.incrementNumWritten();
     }
+  }
+  if (m_storeSumOfPosterior) {
+    // sum over pairs of posterior * expectedCoalTimes[k] (ref: HMM.cpp:1387-1389); the device sums the posteriors,
+    // the weight is applied to the sum (equal to rounding)
+    for (int k = 0; k < S; ++k) {
+      const float e = m_decodingQuant.expectedTimes[k];
+      float* d = out.sumOfPosteriors.row(k);
+      for (int s2 = 0; s2 < L; ++s2) {
+        d[s2] += postSum[static_cast<size_t>(k) * L + s2] * e;
+      }
+    }
+  }
+}
+
+// Posterior sums over all pairs of the job for ASMC's decodeAll (ref: HMM.cpp:1044-1085, augmentSumOverPairs): the
+// device sums the posteriors of a chunk per (site, state) and, for the major/minor sums, per genotype class of the
+// pair at the site; chunks are added up here.  Float atomics: equal to the reference's sequential sums to rounding.
+void HMM::runPosteriorSumChunk(const Pending* pend, const size_t n)
+{
+  const TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), false, data.geneticPositions, data.sites);
+  const int L = data.sites;
+  const int S = static_cast<int>(m_decodingQuant.states);
+  const bool byGenotype = decodingParams.doMajorMinorPosteriorSums;
+  fsmc_decode_request req{};
+  req.numTiles = static_cast<int64_t>(t.pairs.size());
+  req.hapA = t.hapA.data();
+  req.hapB = t.hapB.data();
+  req.tilePairs = t.pairs.data();
+  req.tileFrom = t.from.data();
+  req.tileTo = t.to.data();
+  req.flags = FSMC_SUM_POSTERIOR | (byGenotype ? FSMC_SUM_BY_GENOTYPE : 0u) | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
+  const size_t plane = static_cast<size_t>(S) * L;
+  std::vector<float> sums((byGenotype ? 3 : 1) * plane);
+  req.sumPosterior = sums.data();
+  fsmc_decode_stats st{};
+  const double t0 = now();
+  check(fsmc_decode(m_ctx, &req, &st), "fsmc_decode");
+  m_stats.decodeWallS += now() - t0;
+  m_stats.decodeCalls += 1;
+  m_stats.pairsDecoded += n;
+  m_stats.batches += (n + m_batchSize - 1) / m_batchSize;
+  m_stats.pairSites += st.pairSites;
+  m_stats.kernelMs += st.kernelMs;
+  m_stats.deviceMs += st.totalMs;
+  auto& out = m_decodingReturnValues;
+  auto addPlane = [&](RowMajorMatrix<float>& dst, const float* src) {
+    for (int k = 0; k < S; ++k) {
+      for (int pos = 0; pos < L; ++pos) {
+        dst(pos, k) += src[static_cast<size_t>(k) * L + pos];
+      }
+    }
+  };
+  if (byGenotype) {
+    addPlane(out.sumOverPairs00, &sums[0]);
+    addPlane(out.sumOverPairs01, &sums[plane]);
+    addPlane(out.sumOverPairs11, &sums[2 * plane]);
+    if (decodingParams.doPosteriorSums) {
+      for (int c = 0; c < 3; ++c) {
+        addPlane(out.sumOverPairs, &sums[c * plane]);
+      }
+    }
+  } else {
+    addPlane(out.sumOverPairs, &sums[0]);
   }
 }
 

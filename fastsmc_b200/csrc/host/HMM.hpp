@@ -33,6 +33,10 @@ struct PairObservations {
 
 // ref: HMM.hpp:54-64.  Sum-over-pairs posteriors are not produced by this build.
 struct DecodingReturnValues {
+  /// sum of posteriors over all decoded pairs, sites x states (ref: HMM.hpp:52); filled when doPosteriorSums
+  RowMajorMatrix<float> sumOverPairs;
+  /// the same restricted to pairs that are both-major / heterozygous / both-minor at the site (doMajorMinorPosteriorSums)
+  RowMajorMatrix<float> sumOverPairs00, sumOverPairs01, sumOverPairs11;
   int sites = 0;
   unsigned int states = 0;
   std::vector<bool> siteWasFlippedDuringFolding = {};
@@ -163,6 +167,7 @@ private:
   void flushPending(bool all);
   void runSegmentChunk(const Pending* pairs, size_t n);
   void runPerSiteChunk(const Pending* pairs, const unsigned long* rows, size_t n);
+  void runPosteriorSumChunk(const Pending* pairs, size_t n);
   IbdSegment toIbdSegment(const SegmentBlock& block, size_t i) const;
   void formatSegments(const SegmentBlock& block, size_t lo, size_t hi, std::string& out) const;
   double m_segmentsPerPair = 4.0;  // densest chunk so far: sizes the next chunk's record buffer

@@ -72,6 +72,22 @@ PYBIND11_MODULE(pyASMC, m)
       .value("array", DecodingMode::array);
 
   py::class_<DecodingReturnValues>(m, "DecodingReturnValues")
+      .def_property_readonly("sumOverPairs",
+                             [](py::object self) {
+                               return matrixView(self.cast<DecodingReturnValues&>().sumOverPairs, self);
+                             })
+      .def_property_readonly("sumOverPairs00",
+                             [](py::object self) {
+                               return matrixView(self.cast<DecodingReturnValues&>().sumOverPairs00, self);
+                             })
+      .def_property_readonly("sumOverPairs01",
+                             [](py::object self) {
+                               return matrixView(self.cast<DecodingReturnValues&>().sumOverPairs01, self);
+                             })
+      .def_property_readonly("sumOverPairs11",
+                             [](py::object self) {
+                               return matrixView(self.cast<DecodingReturnValues&>().sumOverPairs11, self);
+                             })
       .def_readwrite("sites", &DecodingReturnValues::sites)
       .def_readwrite("states", &DecodingReturnValues::states)
       .def_readwrite("siteWasFlippedDuringFolding", &DecodingReturnValues::siteWasFlippedDuringFolding);

@@ -6,7 +6,8 @@
 // words and touches every matching pair at every word.  Here the interval structure is computed order-free:
 //
 //   transposeWordsKernel : [hap][word] packed haplotypes -> [word][hap] keys (coalesced for the per-word passes)
-//   per word w:
+//   per word w (words are independent: a launch handles a batch of words, blockIdx.y = word within the batch, each
+//   word with its own slice of the scratch tables, so that small sample counts are not bound by launch latency):
 //     groupInsertKernel  : open-addressing hash on the 64-bit word itself (the reference's hash is the identity on
 //                          the word, so equal key <=> identical word: no false positives); a slot is owned by the
 //                          first haplotype that claims it; every haplotype gets (slot, rank within slot)
@@ -47,22 +48,43 @@ struct SeedArgs {
   uint32_t loI, hiI, loJ, hiJ;
   int lastJob, aboveDiag;
   unsigned flags;
-  // per-word scratch
+  // per-word scratch; word j of a batch uses slice j of every table (strides C, H, maxGroups, maxGroups + 1)
   uint32_t* owner;           // [C] hap+1 owning the slot, 0 = empty
   uint32_t* slotCount;       // [C]
   uint32_t* slotGroup;       // [C]
   uint32_t C;                // power of two
   uint32_t* slotOf;          // [H]
   uint32_t* rankOf;          // [H]
-  uint32_t* groupSize;       // [H/2+1]
-  uint32_t* groupMemberBase; // [H/2+1]
-  unsigned long long* groupPairBase;  // [H/2+2]  (exclusive scan, last = total)
+  uint32_t* groupSize;       // [maxGroups]
+  uint32_t* groupMemberBase; // [maxGroups]
+  unsigned long long* groupPairBase;  // [maxGroups + 1]  (exclusive scan, last = total)
   uint32_t* members;         // [H]
-  unsigned long long* counters;  // [0] numGroups [1] pairCursor [2] totalPairs(word) [3] matchCount [4] pairVisits
-                                 // [5] numStarts
+  uint32_t maxGroups;
+  unsigned long long* wordCounters;  // [word in batch][4]: [0] numGroups [1] pairCursor [2] totalPairs
+  unsigned long long* counters;      // whole job: [3] matchCount [4] pairVisits [5] numStarts
+  int wordBase;              // first word of the batch
+  int wordsInBatch;
+  unsigned long long* batchChunkBase;  // [wordsInBatch + 1] exclusive scan of the words' chunk counts, then [+1] cursor
   fsmc_match* out;
   long long capacity;
 };
+
+// The tables of word j of the batch.
+__device__ __forceinline__ SeedArgs wordSlice(const SeedArgs& a, const uint32_t j)
+{
+  SeedArgs v = a;
+  v.owner += static_cast<size_t>(j) * a.C;
+  v.slotCount += static_cast<size_t>(j) * a.C;
+  v.slotGroup += static_cast<size_t>(j) * a.C;
+  v.slotOf += static_cast<size_t>(j) * a.H;
+  v.rankOf += static_cast<size_t>(j) * a.H;
+  v.members += static_cast<size_t>(j) * a.H;
+  v.groupSize += static_cast<size_t>(j) * a.maxGroups;
+  v.groupMemberBase += static_cast<size_t>(j) * a.maxGroups;
+  v.groupPairBase += static_cast<size_t>(j) * (a.maxGroups + 1);
+  v.wordCounters += static_cast<size_t>(j) * 4;
+  return v;
+}
 
 __device__ __forceinline__ uint32_t mixKey(uint64_t k)
 {
@@ -96,8 +118,10 @@ __global__ void transposeWordsKernel(const uint64_t* __restrict__ haps, const lo
   }
 }
 
-__global__ void groupInsertKernel(const SeedArgs a, const int w)
+__global__ void groupInsertKernel(const SeedArgs args)
 {
+  const SeedArgs a = wordSlice(args, blockIdx.y);
+  const int w = args.wordBase + static_cast<int>(blockIdx.y);
   const uint64_t* keys = a.keysT + static_cast<size_t>(w) * a.H;
   for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
     const uint64_t k = keys[h];
@@ -120,12 +144,13 @@ __global__ void groupInsertKernel(const SeedArgs a, const int w)
   }
 }
 
-__global__ void groupCompactKernel(const SeedArgs a)
+__global__ void groupCompactKernel(const SeedArgs args)
 {
+  const SeedArgs a = wordSlice(args, blockIdx.y);
   for (uint32_t s = blockIdx.x * blockDim.x + threadIdx.x; s < a.C; s += gridDim.x * blockDim.x) {
     const uint32_t n = a.slotCount[s];
     if (n >= 2u) {
-      const uint32_t g = static_cast<uint32_t>(atomicAdd(&a.counters[0], 1ull));
+      const uint32_t g = static_cast<uint32_t>(atomicAdd(&a.wordCounters[0], 1ull));
       a.slotGroup[s] = g;
       a.groupSize[g] = n;
     }
@@ -133,10 +158,11 @@ __global__ void groupCompactKernel(const SeedArgs a)
 }
 
 // One CTA: exclusive scans over the groups (member offsets, pair offsets).  Each thread owns a contiguous run.
-__global__ void groupScanKernel(const SeedArgs a)
+__global__ void groupScanKernel(const SeedArgs args)
 {
+  const SeedArgs a = wordSlice(args, blockIdx.x);
   __shared__ unsigned long long partMembers[1024], partPairs[1024];
-  const uint32_t G = static_cast<uint32_t>(a.counters[0]);
+  const uint32_t G = static_cast<uint32_t>(a.wordCounters[0]);
   const uint32_t T = blockDim.x, t = threadIdx.x;
   const uint32_t per = (G + T - 1) / T;
   const uint32_t lo = min(G, t * per), hi = min(G, lo + per);
@@ -159,9 +185,9 @@ __global__ void groupScanKernel(const SeedArgs a)
       rp += xp;
     }
     a.groupPairBase[G] = rp;
-    a.counters[2] = rp;
-    a.counters[1] = 0ull;
-    a.counters[4] += rp;
+    a.wordCounters[2] = rp;
+    a.wordCounters[1] = 0ull;
+    atomicAdd(&a.counters[4], rp);
   }
   __syncthreads();
   m = partMembers[t];
@@ -175,13 +201,33 @@ __global__ void groupScanKernel(const SeedArgs a)
   }
 }
 
-__global__ void groupScatterKernel(const SeedArgs a)
+__global__ void groupScatterKernel(const SeedArgs args)
 {
+  const SeedArgs a = wordSlice(args, blockIdx.y);
   for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
     const uint32_t s = a.slotOf[h];
     if (a.slotCount[s] >= 2u) {
       a.members[a.groupMemberBase[a.slotGroup[s]] + a.rankOf[h]] = h;
     }
+  }
+}
+
+constexpr int kPairChunk = 8;        // consecutive pair indices per thread
+constexpr int kPairBlockThreads = 256;
+constexpr unsigned long long kPairsPerChunk = static_cast<unsigned long long>(kPairChunk) * kPairBlockThreads;
+
+// One warp: the pair space of every word of the batch is cut into chunks of kPairsPerChunk pairs; the chunks of all
+// words form one queue (exclusive scan of the chunk counts), so that pairExtendKernel's CTAs balance across words.
+__global__ void batchChunksKernel(const SeedArgs a)
+{
+  if (threadIdx.x == 0) {
+    unsigned long long run = 0;
+    for (int j = 0; j < a.wordsInBatch; ++j) {
+      a.batchChunkBase[j] = run;
+      run += (a.wordCounters[static_cast<size_t>(j) * 4 + 2] + kPairsPerChunk - 1) / kPairsPerChunk;
+    }
+    a.batchChunkBase[a.wordsInBatch] = run;
+    a.batchChunkBase[a.wordsInBatch + 1] = 0ull;  // queue head
   }
 }
 
@@ -198,25 +244,41 @@ __device__ __forceinline__ bool pairInJob(const SeedArgs& a, const uint32_t hi, 
   return false;
 }
 
-constexpr int kPairChunk = 8;  // consecutive pair indices per thread
-
-__global__ void __launch_bounds__(256) pairExtendKernel(const SeedArgs a, const int w)
+__global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const SeedArgs args)
 {
   const unsigned lane = threadIdx.x & 31u;
-  const unsigned long long total = a.counters[2];
-  const uint32_t G = static_cast<uint32_t>(a.counters[0]);
-  __shared__ unsigned long long blockBase;
-  const unsigned long long perBlock = static_cast<unsigned long long>(blockDim.x) * kPairChunk;
+  __shared__ unsigned long long blockChunk;
+  __shared__ unsigned long long chunkBase[65];
+  for (int j = threadIdx.x; j <= args.wordsInBatch; j += blockDim.x) {
+    chunkBase[j] = args.batchChunkBase[j];
+  }
+  __syncthreads();
+  const unsigned long long totalChunks = chunkBase[args.wordsInBatch];
   for (;;) {
     __syncthreads();
     if (threadIdx.x == 0) {
-      blockBase = atomicAdd(&a.counters[1], perBlock);
+      blockChunk = atomicAdd(&args.batchChunkBase[args.wordsInBatch + 1], 1ull);
     }
     __syncthreads();
-    const unsigned long long base = blockBase;
-    if (base >= total) {
+    const unsigned long long chunk = blockChunk;
+    if (chunk >= totalChunks) {
       break;
     }
+    // word of this chunk: last j with chunkBase[j] <= chunk (at most 64 words per batch)
+    int j = 0;
+    for (int step = 32; step > 0; step >>= 1) {
+      if (j + step < args.wordsInBatch && chunkBase[j + step] <= chunk) {
+        j += step;
+      }
+    }
+    while (j + 1 < args.wordsInBatch && chunkBase[j + 1] <= chunk) {
+      ++j;
+    }
+    const SeedArgs a = wordSlice(args, static_cast<uint32_t>(j));
+    const int w = args.wordBase + j;
+    const unsigned long long total = a.wordCounters[2];
+    const uint32_t G = static_cast<uint32_t>(a.wordCounters[0]);
+    const unsigned long long base = (chunk - chunkBase[j]) * kPairsPerChunk;
     unsigned long long q = base + static_cast<unsigned long long>(threadIdx.x) * kPairChunk;
     // locate the group of pair index q: last g with groupPairBase[g] <= q
     uint32_t g = 0, n = 0, memberBase = 0, i = 0, ii = 0;

@@ -109,6 +109,12 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, int64_t numHaps, in
 #define FSMC_GENERIC_KERNEL 0x40u /* force the any-S shared-memory kernel (testing)               */
 #define FSMC_WIDE_KERNEL 0x80u    /* never use the narrow (no beta round trip) kernel (testing)   */
 #define FSMC_ONE_WARP_KERNEL 0x100u /* never use the state-split kernels (one tile per CTA) (testing) */
+#define FSMC_SITE_POSTERIOR 0x200u /* full per-site posterior of every pair (HMM.cpp:1372-1389, ASMC::decodePairs
+                                      per_pair_posteriors; HMM::decode)                             */
+#define FSMC_SUM_POSTERIOR 0x400u  /* per-site posterior summed over the real pairs of the call
+                                      (augmentSumOverPairs, HMM.cpp:1044-1085; sum_of_posteriors)   */
+#define FSMC_SUM_BY_GENOTYPE 0x800u /* with FSMC_SUM_POSTERIOR: three sums, by the pair's genotype at the site:
+                                      both major / heterozygous / both minor (sumOverPairs00/01/11)  */
 
 typedef struct fsmc_segment {
   uint32_t pair;     /* tile * 32 + lane                                                        */
@@ -140,6 +146,13 @@ typedef struct fsmc_decode_request {
   int32_t* siteMap;
   float* siteIbd;
   int64_t siteStride;
+  /* FSMC_SITE_POSTERIOR: row-major [numTiles*32][states][siteStride], column = pos - tileFrom.      */
+  float* sitePosterior;
+  /* FSMC_SUM_POSTERIOR: row-major [planes][states][sites], column = absolute site; planes = 3 with
+   * FSMC_SUM_BY_GENOTYPE (0: both major, 1: heterozygous, 2: both minor), else 1.  Overwritten with
+   * the sums of THIS call (float atomics on the device: the summation order is not fixed, results
+   * agree with the reference's sequential sums to rounding).                                        */
+  float* sumPosterior;
 } fsmc_decode_request;
 
 typedef struct fsmc_decode_stats {

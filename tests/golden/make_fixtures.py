@@ -8,6 +8,9 @@ What it writes (all are DATA files of the reference, copied or row-filtered; no 
   tests/golden/fastsmc_example/regression_output{,_no_hashing}.ibd.gz the reference's golden outputs G1 / G2
   tests/golden/asmc_example/exampleFile.n300.array.{hap.gz,samples,map.gz}   FILES/EXAMPLE
   tests/golden/binary_output.bibd.gz                                  ASMC_SRC/TESTS/data (binary reader fixture)
+  tests/golden/asmc_sum_over_pairs.gz                                 ASMC_SRC/TESTS/data/regression_test_original.gz: the
+                                                                      reference's golden sumOverPairs (6760 sites x 69 states)
+                                                                      of ASMC_SRC/TESTS/test_regression.cpp (golden G4)
   data/30-100-2000.decodingQuantities.gz                              row-filtered copy of FILES/DECODING_QUANTITIES
   data/ukbb_maf.npz                                                   MAF column of FILES/UKBB.frq for chr 1 (first 50k), 20, 22
 
@@ -110,6 +113,7 @@ def main():
     for f in ("exampleFile.n300.array.hap.gz", "exampleFile.n300.array.samples", "exampleFile.n300.array.map.gz"):
         shutil.copyfile(A + f, os.path.join(ax, f))
     shutil.copyfile(REF + "/ASMC_SRC/TESTS/data/binary_output.bibd.gz", os.path.join(HERE, "binary_output.bibd.gz"))
+    shutil.copyfile(REF + "/ASMC_SRC/TESTS/data/regression_test_original.gz", os.path.join(HERE, "asmc_sum_over_pairs.gz"))
 
     o = Oracle(E + "example", E + "example.decodingQuantities.gz", "/tmp/x", hashing=True, time=50)
     keys = needed_keys(o.positions()[0])

@@ -1,12 +1,12 @@
 """Developer probe (not the bench): times the decode kernels on a synthetic all-pairs job, with model tables
-taken from the oracle.  Usage: python tools/perf_probe.py [n_haps] [n_sites] [dq: 69|159] [n_pairs]"""
+taken from the oracle.  Usage: python tests/probes/perf_probe.py [n_haps] [n_sites] [dq: 69|159] [n_pairs]"""
 import os
 import sys
 import time
 
 import numpy as np
 
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tests"))
 from conftest import DQ_69, FASTSMC_EXAMPLE_DQ, context_from_oracle  # noqa: E402

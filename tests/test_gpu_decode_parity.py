@@ -59,6 +59,40 @@ def test_per_site_outputs_fast_mode_within_tolerance(example, generic):
     assert (r.site_map[rows, :to - frm] != mp).mean() < 1e-3
 
 
+@pytest.mark.parametrize("generic", [False, True])
+def test_full_posteriors_and_sum_over_pairs(example, generic):
+    """FSMC_SITE_POSTERIOR: the whole posterior of every pair (what HMM::decode / decodePairs(per_pair_posteriors)
+    return), bit-identical in exact mode.  FSMC_SUM_POSTERIOR: its sum over the real pairs of the call
+    (augmentSumOverPairs, ref HMM.cpp:1044-1085), by genotype class with FSMC_SUM_BY_GENOTYPE; float atomics, so
+    compared at 1e-5 relative."""
+    from fastsmc_b200 import _native as N
+    o, ctx = example
+    rng = np.random.default_rng(5)
+    a, b = _pairs(rng, 40, o.num_haps)  # 40 pairs: a full tile and a ragged one (padding lanes must not be summed)
+    frm, to = 2000, 2300
+    want = o.decode_posterior(a, b, frm, to)  # [pair][site][state]
+    tiles = ctx.make_tiles(a, b, windows=[[frm, to], [frm, to]], sites=o.sites)
+    kernel = N.GENERIC_KERNEL if generic else 0
+    r = ctx.decode(tiles, N.SITE_POSTERIOR | N.SUM_POSTERIOR | N.EXACT | kernel)
+    got = r.site_posterior[tiles["rows"], :, :to - frm].transpose(0, 2, 1)
+    assert np.array_equal(got.view(np.uint32), want.view(np.uint32))
+    total = want.astype(np.float64).sum(axis=0).T  # [state][site]
+    assert r.sum_posterior.shape == (1, o.states, o.sites)
+    np.testing.assert_allclose(r.sum_posterior[0][:, frm:to], total, rtol=1e-5)
+    assert not r.sum_posterior[0][:, :frm].any() and not r.sum_posterior[0][:, to:].any()
+    np.testing.assert_allclose(r.sum_posterior[0][:, frm:to].sum(axis=0), len(a), rtol=1e-5)  # posteriors sum to 1
+
+    # by genotype class of the pair at the site: 0 both major, 1 heterozygous, 2 both minor (folded alleles)
+    haps = np.asarray(o.haplotypes())[:, frm:to].astype(bool)
+    ha, hb = haps[a], haps[b]
+    cls = np.where(ha ^ hb, 1, np.where(ha & hb, 2, 0))  # [pair][site]
+    r3 = ctx.decode(tiles, N.SUM_POSTERIOR | N.SUM_BY_GENOTYPE | kernel)  # FMA arithmetic: 1e-4
+    assert r3.sum_posterior.shape == (3, o.states, o.sites)
+    for c in range(3):
+        part = (want.astype(np.float64) * (cls == c)[:, :, None]).sum(axis=0).T
+        np.testing.assert_allclose(r3.sum_posterior[c][:, frm:to], part, rtol=REL_TOL, atol=1e-7)
+
+
 def _oracle_segments(o):
     ints, floats = o.segments()
     return ints, floats
@@ -227,6 +261,26 @@ def test_fast_kernel_segments_69_states(synthetic69, split):
     np.testing.assert_allclose(g[:, 0], w[:, 0], rtol=REL_TOL)
     np.testing.assert_allclose(g[:, 1], w[:, 1], rtol=REL_TOL)
     assert (g[:, 2] != w[:, 2]).mean() < 5e-3
+
+
+def test_segment_records_do_not_depend_on_previous_buffer_contents(synthetic69):
+    """fsmc_decode sorts the records into the caller's buffer; what the buffer held before the call must not matter.
+    (A reused heap block holds the records of an earlier call: same pair numbering, other positions.)"""
+    from fastsmc_b200 import _native as N
+    o, ctx = synthetic69
+    ia, ib = np.triu_indices(64, 1)
+    tiles = ctx.make_tiles(ia.astype(np.uint32), ib.astype(np.uint32), sites=o.sites)
+    flags = N.CALL_SEGMENTS | N.SEG_AGE
+    clean = ctx.decode(tiles, flags, segment_capacity=1 << 16).segments.copy()
+    assert len(clean) > 100
+    # adversarial previous contents: every slot holds the record that belongs one slot further, moved to a later site
+    stale = np.zeros(1 << 16, N.SEGMENT_DTYPE)
+    stale[:len(clean) - 1] = clean[1:]
+    stale["posStart"] += 1 << 20
+    again = ctx.decode(tiles, flags, segment_capacity=1 << 16, segment_prefill=stale).segments
+    assert again.tobytes() == clean.tobytes()
+    key = clean["pair"].astype(np.int64) * (1 << 32) + clean["posStart"]
+    assert (np.diff(key) > 0).all()  # sorted by (pair, start), every record once
 
 
 def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69, split):
