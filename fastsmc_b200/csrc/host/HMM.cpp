@@ -800,14 +800,46 @@ void HMM::runPosteriorSumChunk(const Pending* pend, const size_t n)
   }
 }
 
-std::vector<std::vector<float>> HMM::decode(const PairObservations&)
+// ref: HMM.cpp:1464-1495 — the whole posterior of one pair, [state][site - from]
+std::vector<std::vector<float>> HMM::decode(const PairObservations& obs)
 {
-  throw std::runtime_error("HMM::decode (full posterior matrix of one pair) is not produced by the B200 build");
+  return decode(obs, 0u, static_cast<unsigned>(data.sites));
 }
 
-std::vector<std::vector<float>> HMM::decode(const PairObservations&, unsigned, unsigned)
+std::vector<std::vector<float>> HMM::decode(const PairObservations& obs, const unsigned from, const unsigned to)
 {
-  throw std::runtime_error("HMM::decode (full posterior matrix of one pair) is not produced by the B200 build");
+  if (from >= to || to > static_cast<unsigned>(data.sites)) {
+    throw std::runtime_error("HMM::decode: window out of range");
+  }
+  const int S = static_cast<int>(m_decodingQuant.states);
+  const int len = static_cast<int>(to - from);
+  std::vector<uint32_t> hapA(FSMC_TILE, 0u), hapB(FSMC_TILE, 0u);
+  hapA[0] = static_cast<uint32_t>(asmc::dipToHapId(obs.iInd, obs.iHap));
+  hapB[0] = static_cast<uint32_t>(asmc::dipToHapId(obs.jInd, obs.jHap));
+  const int32_t one = 1, f = static_cast<int32_t>(from), e = static_cast<int32_t>(to);
+  fsmc_decode_request req{};
+  req.numTiles = 1;
+  req.hapA = hapA.data();
+  req.hapB = hapB.data();
+  req.tilePairs = &one;
+  req.tileFrom = &f;
+  req.tileTo = &e;
+  const bool sums = decodingParams.doPosteriorSums;
+  req.flags = FSMC_SITE_POSTERIOR | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
+  std::vector<float> post(static_cast<size_t>(FSMC_TILE) * S * len);
+  req.sitePosterior = post.data();
+  req.siteStride = len;
+  check(fsmc_decode(m_ctx, &req, nullptr), "fsmc_decode");
+  std::vector<std::vector<float>> out(static_cast<size_t>(S));
+  for (int k = 0; k < S; ++k) {
+    out[k].assign(post.begin() + static_cast<size_t>(k) * len, post.begin() + static_cast<size_t>(k + 1) * len);
+    if (sums) {
+      for (int pos = 0; pos < len; ++pos) {
+        m_decodingReturnValues.sumOverPairs(static_cast<long>(from) + pos, k) += out[k][pos];
+      }
+    }
+  }
+  return out;
 }
 
 // ref: HMM.cpp:1532-1560

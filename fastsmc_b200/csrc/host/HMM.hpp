@@ -31,7 +31,7 @@ struct PairObservations {
   std::vector<bool> homMinorBits;
 };
 
-// ref: HMM.hpp:54-64.  Sum-over-pairs posteriors are not produced by this build.
+// ref: HMM.hpp:45-64.
 struct DecodingReturnValues {
   /// sum of posteriors over all decoded pairs, sites x states (ref: HMM.hpp:52); filled when doPosteriorSums
   RowMajorMatrix<float> sumOverPairs;

@@ -212,13 +212,14 @@ def test_asmc_decode_pairs_full_posteriors_and_sum(asmc, oracle_mod):
 
 def test_asmc_decode_all_posterior_sums_vs_reference_golden(asmc):
     """ASMC decodeAll with doPosteriorSums on the bundled 150-sample array data (all 44 850 haplotype pairs) against
-    the reference's own golden sumOverPairs (ASMC_SRC/TESTS/test_regression.cpp:23-67, golden G4).  The golden was made
-    without a fixed seed (the undistinguished-count draws of the emission tables differ), so the comparison is loose
-    (G4_TOL below, measured with the CPU oracle); row sums are exact properties: every site's posteriors of all
-    pairs sum to the number of pairs.  The major/minor sums partition the total."""
+    the reference's own golden sumOverPairs (ASMC_SRC/TESTS/test_regression.cpp:23-67, golden G4, printed at 6
+    significant digits).  The CPU oracle reproduces the golden to 7.8e-6 (L1) / 1.2e-4 (worst element)
+    (tests/probes/g4_oracle_check.py); the GPU path (FMA arithmetic, float atomics) is held to the north-star 1e-4 on
+    the L1 difference.  Row sums are exact properties: every site's posteriors of all pairs sum to the number of
+    pairs.  The major/minor sums partition the total."""
     import gzip
     import os
-    G4_TOL = 0.02
+    G4_TOL = 1e-4
     p = asmc.DecodingParams(ASMC_EXAMPLE, DQ_69, "", 1, 1, "array", False, True, False, False, 0.0, False, True)
     p.useKnownSeed = True
     p.verbose = False
@@ -228,7 +229,31 @@ def test_asmc_decode_all_posterior_sums_vs_reference_golden(asmc):
     gold = np.loadtxt(gzip.open(os.path.join(GOLDEN, "asmc_sum_over_pairs.gz"), "rt"))
     assert got.shape == gold.shape == (6760, 69)
     np.testing.assert_allclose(got.sum(axis=1), 44850.0, rtol=2e-4)
-    assert np.abs(got - gold).sum() / gold.sum() < G4_TOL
+    l1 = np.abs(got - gold).sum() / gold.sum()
+    worst = (np.abs(got - gold) / np.maximum(gold, 1e-3)).max()
+    print(f"G4: L1 relative difference {l1:.3e}, worst element {worst:.3e}")
+    assert l1 < G4_TOL and worst < 2e-3, (l1, worst)
     parts = np.array(r.sumOverPairs00, dtype=np.float64) + np.array(r.sumOverPairs01) + np.array(r.sumOverPairs11)
     np.testing.assert_allclose(parts, got, rtol=1e-5, atol=1e-4)
     assert np.array(r.sumOverPairs01).sum() > 0 and np.array(r.sumOverPairs11).sum() > 0
+
+
+def test_hmm_decode_returns_full_posterior_of_one_pair(asmc, oracle_mod):
+    """HMM::decode(obs, from, to) (ref: HMM.cpp:1464-1495): states x sites posterior of one pair, bit-identical to the
+    oracle in exact mode; decodeSummarize's posterior mean is its expectation."""
+    p = asmc.DecodingParams(ASMC_EXAMPLE, DQ_69, "", 1, 1, "array", False, True)
+    p.useKnownSeed = True
+    p.exactArithmetic = True
+    p.verbose = False
+    hmm = asmc.HMM(asmc.Data(p), p)
+    obs = hmm.makePairObs(1, 0, 2, 5)  # haplotype 1 of individual 0 vs haplotype 2 of individual 5
+    got = np.array(hmm.decode(obs, 100, 900), dtype=np.float32)
+    o = oracle_mod.Oracle(ASMC_EXAMPLE, DQ_69, "/tmp/x", hashing=False, FastSMC=False, asmcMode=True, batchSize=64,
+                          useKnownSeed=True)
+    want = o.decode_posterior(np.array([0]), np.array([11]), 100, 900)[0].T
+    assert got.shape == want.shape == (o.states, 800)
+    assert np.array_equal(got.view(np.uint32), np.ascontiguousarray(want).view(np.uint32))
+    np.testing.assert_allclose(got.sum(axis=0), 1.0, rtol=1e-5)
+    whole = np.array(hmm.decode(obs), dtype=np.float32)
+    mean, _ = hmm.decodeSummarize(obs)
+    np.testing.assert_allclose((whole * o.vector("expectedTimes")[:, None]).sum(axis=0), np.array(mean), rtol=1e-5)
