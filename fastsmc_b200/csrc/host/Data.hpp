@@ -98,5 +98,8 @@ private:
   void allocate();
   void addSite(int pos, const char* alleles /* 2 chars per haplotype: ' ' + '0'/'1' */, unsigned long nHapsInFile,
                bool subset);
+  void flushSiteWord();
+  std::vector<uint64_t> mWordBuf;  // bits of the current 64-site word, one entry per loaded haplotype
+  long mWordBufIndex = -1;
   void addMarker(int pos, unsigned long bp, const std::vector<std::pair<unsigned long, double>>& gmap, unsigned& cur_g);
 };
