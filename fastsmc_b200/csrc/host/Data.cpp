@@ -122,7 +122,9 @@ bool Data::readSample(const unsigned n) const
 Data::Data(const DecodingParams& params)
 {
   const std::string& root = params.inFileRoot;
-  sites = countHapLines(root);
+  // `sites` is set by the reader itself (finishSites): counting the lines first would inflate the whole .hap.gz one
+  // more time, and inflation is what bounds the read (the reference opens the file four times)
+  sites = 0;
   sampleSize = static_cast<unsigned long>(countSamplesLines(root));
   haploidSampleSize = sampleSize * 2ul;
   setJobGeometry(params);
@@ -141,12 +143,14 @@ Data::Data(const DecodingParams& params)
 
 void Data::allocate()
 {
-  wordsPerHap = (sites + 63) / 64;
-  hapBits.assign(static_cast<size_t>(numLoadedHaplotypes()) * wordsPerHap, 0ull);
-  flipMask.assign(wordsPerHap, 0ull);
-  siteWasFlippedDuringFolding.assign(sites, false);
-  totalSamplesCount.assign(sites, 0);
-  derivedAlleleCounts.assign(sites, 0);
+  wordsPerHap = 0;
+  hapBits.clear();
+  flipMask.clear();
+  siteWasFlippedDuringFolding.clear();
+  totalSamplesCount.clear();
+  derivedAlleleCounts.clear();
+  mWordMajor.clear();
+  mWordBufIndex = -1;
   geneticPositions.clear();
   physicalPositions.clear();
   recRateAtMarker.clear();
@@ -225,9 +229,17 @@ void Data::addSite(const int pos, const char* alleles, const unsigned long nHaps
   }
   const int total = static_cast<int>(nHapsInFile);
   const bool minorIsOne = foldToMinorAlleles ? (derived <= total - derived) : true;
-  siteWasFlippedDuringFolding[pos] = !minorIsOne;
   const int shift = pos & 63;
   const long w = pos >> 6;
+  if (static_cast<size_t>(pos) >= totalSamplesCount.size()) {
+    siteWasFlippedDuringFolding.resize(pos + 1, false);
+    totalSamplesCount.resize(pos + 1, 0);
+    derivedAlleleCounts.resize(pos + 1, 0);
+  }
+  if (static_cast<size_t>(w) >= flipMask.size()) {
+    flipMask.resize(w + 1, 0ull);
+  }
+  siteWasFlippedDuringFolding[pos] = !minorIsOne;
   if (!minorIsOne) {
     flipMask[w] |= 1ull << shift;
   }
@@ -253,18 +265,47 @@ void Data::addSite(const int pos, const char* alleles, const unsigned long nHaps
   derivedAlleleCounts[pos] = foldToMinorAlleles ? std::min(derived, total - derived) : derived;
 }
 
-// Writes the collected word of every loaded haplotype into the hap-major matrix.  Called when the next word starts
-// and after the last site.
+// Appends the collected word of every loaded haplotype to the word-major store.  Called when the next word starts and
+// by finishSites.
 void Data::flushSiteWord()
 {
   if (mWordBufIndex < 0) {
     return;
   }
-  const size_t n = mWordBuf.size();
-  for (size_t l = 0; l < n; ++l) {
-    hapBits[l * wordsPerHap + mWordBufIndex] |= mWordBuf[l];
+  if (static_cast<size_t>(mWordBufIndex) * mWordBuf.size() != mWordMajor.size()) {
+    std::cerr << "ERROR: sites must be added in ascending order" << std::endl;
+    exit(1);
   }
+  mWordMajor.insert(mWordMajor.end(), mWordBuf.begin(), mWordBuf.end());
   mWordBufIndex = -1;
+}
+
+// After the last site: fixes the site count and turns the word-major store [word][hap] into the hap-major matrix
+// [hap][word] that the decoder uploads.
+void Data::finishSites(const int numSites)
+{
+  flushSiteWord();
+  sites = numSites;
+  wordsPerHap = (sites + 63) / 64;
+  const size_t H = numLoadedHaplotypes();
+  hapBits.assign(H * wordsPerHap, 0ull);
+  flipMask.resize(wordsPerHap, 0ull);
+  siteWasFlippedDuringFolding.resize(sites, false);
+  totalSamplesCount.resize(sites, 0);
+  derivedAlleleCounts.resize(sites, 0);
+  const size_t W = H ? mWordMajor.size() / H : 0;
+  constexpr size_t kTile = 64;  // transpose in tiles: both sides stay within a few cache lines per row
+  for (size_t w0 = 0; w0 < W; w0 += kTile) {
+    const size_t w1 = std::min(W, w0 + kTile);
+    for (size_t l = 0; l < H; ++l) {
+      uint64_t* dst = hapBits.data() + l * wordsPerHap;
+      for (size_t w = w0; w < w1; ++w) {
+        dst[w] = mWordMajor[w * H + l];
+      }
+    }
+  }
+  std::vector<uint64_t>().swap(mWordMajor);
+  std::vector<uint64_t>().swap(mWordBuf);
 }
 
 // ref: Data.cpp:523-565 (readGeneticMap + addMarker): linear interpolation of the map at bp
@@ -361,7 +402,7 @@ void Data::readHapsFastSMC(const std::string& inFileRoot, const std::vector<std:
     addSite(pos, line.c_str() + off, haploidSampleSize, true);
     ++pos;
   }
-  flushSiteWord();
+  finishSites(pos);
   std::cout << "Read " << pos << " markers" << std::endl;
 }
 
@@ -384,7 +425,7 @@ void Data::readHapsAsmc(const std::string& inFileRoot)
     addSite(pos, line.c_str() + off, haploidSampleSize, false);
     ++pos;
   }
-  flushSiteWord();
+  finishSites(pos);
 }
 
 // ref: Data.cpp:162-210 — PLINK-style map: chr, snp, cM, bp
@@ -450,7 +491,7 @@ Data Data::fromArrays(const DecodingParams& params, const std::vector<std::strin
     d.addMarker(s, static_cast<unsigned long>(physPos[s]), gmap, g);
     d.addSite(s, text.c_str(), d.haploidSampleSize, true);
   }
-  d.flushSiteWord();
+  d.finishSites(numSites);
   return d;
 }
 

@@ -99,7 +99,9 @@ private:
   void addSite(int pos, const char* alleles /* 2 chars per haplotype: ' ' + '0'/'1' */, unsigned long nHapsInFile,
                bool subset);
   void flushSiteWord();
-  std::vector<uint64_t> mWordBuf;  // bits of the current 64-site word, one entry per loaded haplotype
+  void finishSites(int numSites);
+  std::vector<uint64_t> mWordBuf;    // bits of the current 64-site word, one entry per loaded haplotype
+  std::vector<uint64_t> mWordMajor;  // completed words, [word][hap]; transposed into hapBits by finishSites
   long mWordBufIndex = -1;
   void addMarker(int pos, unsigned long bp, const std::vector<std::pair<unsigned long, double>>& gmap, unsigned& cur_g);
 };
