@@ -1046,7 +1046,15 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   }
   ctx->seedCacheValid = false;  // consumed by this call
   const long long stored = found;
-  if (stored > 0) {
+  if (stored > 0 && (sp->flags & FSMC_SEED_UNSORTED)) {
+    FSMC_CUDA(cudaMemcpyAsync(out, ctx->seedOut.p, stored * sizeof(fsmc_match), cudaMemcpyDeviceToHost, st));
+    FSMC_CUDA(cudaStreamSynchronize(st));
+    for (long long i = 0; i < stored; ++i) {
+      if (out[i].endWord < out[i].startWord || out[i].startWord < 0 || out[i].endWord >= static_cast<int>(ctx->sites / 64)) {
+        return fail(FSMC_E_CUDA, "fsmc_seed: corrupt match record (words %d..%d)", out[i].startWord, out[i].endWord);
+      }
+    }
+  } else if (stored > 0) {
     // canonical candidate order (endWord, hapA, hapB): counting sort by end word from a staging copy into the
     // caller's buffer, then every end-word bucket is sorted by pair on its own host thread
     std::vector<fsmc_match> stage(static_cast<size_t>(stored));
@@ -1096,18 +1104,29 @@ int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats
   }
   FSMC_CUDA(cudaSetDevice(ctx->device));
   FSMC_CUDA(cudaEventRecord(ctx->ev[0], ctx->stream));
+  static const bool trace = std::getenv("FSMC_TRACE") != nullptr;  // development: host time of the call's phases
+  const auto t0 = std::chrono::steady_clock::now();
   fsmc_plan* plan = nullptr;
   int rc = fsmc_plan_create(ctx, req, &plan);
   if (rc != FSMC_OK) {
     return rc;
   }
+  const auto t1 = std::chrono::steady_clock::now();
   rc = fsmc_plan_launch(ctx, plan);
+  const auto t2 = std::chrono::steady_clock::now();
   if (rc == FSMC_OK) {
     rc = fsmc_plan_collect(ctx, plan, req, stats);
   }
+  const auto t3 = std::chrono::steady_clock::now();
   const std::string keep = gLastError;
   fsmc_plan_destroy(ctx, plan);
   gLastError = keep;
+  if (trace) {
+    const auto ms = [](auto a, auto b) { return std::chrono::duration<double, std::milli>(b - a).count(); };
+    std::fprintf(stderr, "fsmc_decode tiles=%lld create %.2f ms launch %.2f ms collect %.2f ms (kernel %.2f ms) destroy %.2f ms\n",
+                 static_cast<long long>(req->numTiles), ms(t0, t1), ms(t1, t2), ms(t2, t3), stats ? stats->kernelMs : 0.f,
+                 ms(t3, std::chrono::steady_clock::now()));
+  }
   return rc;
 }
 

@@ -70,7 +70,8 @@ void ASMC::FastSMC::seedAndDecode()
   sp.hiJ = mData.w_j * mData.windowSize;
   sp.lastJob = lastJob;
   sp.aboveDiag = mData.is_j_above_diag;
-  sp.flags = mParams.referenceCandidateOrder ? FSMC_SEED_ALL_INTERVALS : 0u;
+  // the order replay groups the intervals itself: no need for the canonical sort
+  sp.flags = mParams.referenceCandidateOrder ? (FSMC_SEED_ALL_INTERVALS | FSMC_SEED_UNSORTED) : 0u;
 
   std::vector<fsmc_match> found(std::max<size_t>(1u << 16, static_cast<size_t>(H) * 8));
   const double t0 = now();
@@ -112,8 +113,8 @@ void ASMC::FastSMC::seedAndDecode()
     auto longEnough = [&](const fsmc_match& m) {
       return asmc::cmBetween(m.startWord, m.endWord, mData.geneticPositions, 64) >= static_cast<double>(mParams.min_m);
     };
-    candidate_order::replayReferenceOrder(found, H, W, mParams.gap, rawWord, longEnough,
-                                          [&](const int64_t i) { submit(found[i]); });
+    candidate_order::replayReferenceOrderFast(found, H, W, mParams.gap, rawWord, longEnough,
+                                              [&](const int64_t i) { submit(found[i]); });
     mSeedStats.orderWallS = now() - t1;
   }
   mHmm.finishFromHashing();

@@ -5,6 +5,7 @@
 #include <chrono>
 #include <cmath>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <iostream>
 #include <limits>
@@ -94,6 +95,9 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
   // 8192 reference batches per kernel launch keep every SM busy; batch composition is unaffected because chunks
   // are cut at multiples of the batch size
   m_flushPairs = static_cast<size_t>(m_batchSize) * 8192;
+  if (const char* e = std::getenv("FSMC_FLUSH_BATCHES")) {  // development: reference batches per decode call
+    m_flushPairs = static_cast<size_t>(m_batchSize) * static_cast<size_t>(std::max(1, std::atoi(e)));
+  }
   uploadModel();
 }
 

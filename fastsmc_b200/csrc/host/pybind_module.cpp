@@ -404,23 +404,30 @@ PYBIND11_MODULE(pyASMC, m)
   m.def(
       "replayReferenceOrder",
       [](py::array_t<int64_t, py::array::c_style | py::array::forcecast> intervals, const Data& data, int gap,
-         float min_m) {
+         float min_m, bool fast) {
         std::vector<fsmc_match> iv(intervals.shape(0));
         for (long i = 0; i < intervals.shape(0); ++i) {
           iv[i] = fsmc_match{static_cast<uint32_t>(intervals.at(i, 0)), static_cast<uint32_t>(intervals.at(i, 1)),
                              static_cast<int32_t>(intervals.at(i, 2)), static_cast<int32_t>(intervals.at(i, 3))};
         }
         std::vector<int64_t> order;
-        candidate_order::replayReferenceOrder(
-            iv, static_cast<uint32_t>(data.numLoadedHaplotypes()), data.sites / 64, gap,
-            [&](uint32_t h, int w) { return data.hapBits[static_cast<size_t>(h) * data.wordsPerHap + w] ^ data.flipMask[w]; },
-            [&](const fsmc_match& x) {
-              return asmc::cmBetween(x.startWord, x.endWord, data.geneticPositions, 64) >= static_cast<double>(min_m);
-            },
-            [&](int64_t i) { order.push_back(i); });
+        auto rawWord = [&](uint32_t h, int w) {
+          return data.hapBits[static_cast<size_t>(h) * data.wordsPerHap + w] ^ data.flipMask[w];
+        };
+        auto longEnough = [&](const fsmc_match& x) {
+          return asmc::cmBetween(x.startWord, x.endWord, data.geneticPositions, 64) >= static_cast<double>(min_m);
+        };
+        auto emit = [&](int64_t i) { order.push_back(i); };
+        if (fast) {
+          candidate_order::replayReferenceOrderFast(iv, static_cast<uint32_t>(data.numLoadedHaplotypes()), data.sites / 64,
+                                                    gap, rawWord, longEnough, emit);
+        } else {
+          candidate_order::replayReferenceOrder(iv, static_cast<uint32_t>(data.numLoadedHaplotypes()), data.sites / 64, gap,
+                                                rawWord, longEnough, emit);
+        }
         return order;
       },
-      "intervals"_a, "data"_a, "gap"_a, "min_m"_a);
+      "intervals"_a, "data"_a, "gap"_a, "min_m"_a, "fast"_a = true);
 
   // helpers with reference known-answer tests (ref: ASMC_SRC/TESTS/test_hmm_utils.cpp, test_hashing.cpp)
   m.def("roundMorgans", &asmc::roundMorgans, "value"_a, "precision"_a, "min"_a);

@@ -74,9 +74,9 @@ def write_dataset(root, haps, bp, cm, chrom=1):
     return root
 
 
-def dataset(root, n_haps, n_sites, span_bp, chrom, seed):
+def dataset(root, n_haps, n_sites, span_bp, chrom, seed, founders=None):
     maf = ukbb_maf(chrom, n_sites)
     bp, cm = make_sites(n_sites, span_bp)
-    haps = make_haplotypes(n_haps, maf, cm, seed)
+    haps = make_haplotypes(n_haps, maf, cm, seed, n_founders=founders)
     write_dataset(root, haps, bp, cm, chrom)
     return haps, bp, cm

@@ -203,6 +203,7 @@ int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan);
  * Output order: ascending (endWord, hapA, hapB) — the canonical candidate order.
  * ------------------------------------------------------------------------------------------------ */
 #define FSMC_SEED_ALL_INTERVALS 0x1u /* keep intervals shorter than minLengthCm too (order replay)  */
+#define FSMC_SEED_UNSORTED 0x2u      /* skip the canonical sort: intervals in no particular order     */
 
 typedef struct fsmc_match {
   uint32_t hapA;      /* smaller local haplotype index                                            */

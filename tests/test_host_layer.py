@@ -5,7 +5,7 @@ import os
 import numpy as np
 import pytest
 
-from conftest import FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, GOLDEN, REGRESSION_PARAMS
+from conftest import DQ_69, FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, GOLDEN, REGRESSION_PARAMS
 
 
 @pytest.fixture(scope="module")
@@ -95,11 +95,38 @@ def test_reference_candidate_order_replay(asmc, oracle_mod):
     o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/x", hashing=True, **REGRESSION_PARAMS)
     want = o.seed()
     iv = _brute_force_intervals(d.hapBits, d.sites // 64, p.gap)
-    order = asmc.pyASMC.replayReferenceOrder(iv, d, p.gap, p.min_m)
-    got = iv[np.array(order)]
-    got = np.stack([got[:, 0], got[:, 1], got[:, 2] * 64, got[:, 3] * 64 + 63], axis=1)
-    assert len(got) == len(want) == 495
-    assert np.array_equal(got, want.astype(np.int64))
+    for fast in (False, True):  # the literal replay of the two hash maps, and the production (sort-key) form
+        order = asmc.pyASMC.replayReferenceOrder(iv, d, p.gap, p.min_m, fast=fast)
+        got = iv[np.array(order)]
+        got = np.stack([got[:, 0], got[:, 1], got[:, 2] * 64, got[:, 3] * 64 + 63], axis=1)
+        assert len(got) == len(want) == 495
+        assert np.array_equal(got, want.astype(np.int64))
+    # independent of the order in which the intervals are handed over (the GPU emits them in no particular order)
+    perm = np.random.default_rng(3).permutation(len(iv))
+    order = asmc.pyASMC.replayReferenceOrder(iv[perm], d, p.gap, p.min_m, fast=True)
+    assert np.array_equal(iv[perm][np.array(order)], iv[np.array(asmc.pyASMC.replayReferenceOrder(iv, d, p.gap, p.min_m))])
+
+
+@pytest.mark.parametrize("n_haps,n_sites,gap,min_m", [(240, 3200, 1, 0.0), (400, 1920, 0, 0.05), (150, 6400, 2, 0.4)])
+def test_fast_order_replay_equals_literal_replay_on_dense_matches(asmc, tmp_path, n_haps, n_sites, gap, min_m):
+    """Synthetic data with few founders: hundreds of thousands of short intervals, most of which never become
+    candidates but all of which are nodes of the reference's extend map; the map grows through many rehashes and
+    buckets empty and refill.  The sort-key replay must give the literal replay's sequence."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, n_haps, n_sites, 3000 * n_sites, 1, 77 + n_haps, founders=6)
+    p = asmc.DecodingParams()
+    p.verbose = False
+    p.inFileRoot, p.decodingQuantFile, p.outFileRoot = root, DQ_69, root + ".out"
+    p.decodingModeString, p.foldData, p.usingCSFS, p.FastSMC, p.hashing = "array", True, True, True, True
+    p.gap, p.min_m = gap, min_m
+    p.validateParamsFastSMC()
+    d = asmc.Data(p)
+    iv = _brute_force_intervals(np.array(d.hapBits), d.sites // 64, gap)  # folding flips both haplotypes alike
+    assert len(iv) > 20000
+    slow = asmc.pyASMC.replayReferenceOrder(iv, d, gap, min_m, fast=False)
+    fast = asmc.pyASMC.replayReferenceOrder(iv, d, gap, min_m, fast=True)
+    assert len(slow) > 100 and list(slow) == list(fast)
 
 
 def test_hmm_utils_known_answers(asmc):
