@@ -16,7 +16,10 @@
 
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdint>
+#include <cstdio>
+#include <cstdlib>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -324,6 +327,56 @@ template <class Fn> void parallelForWords(const int numWords, unsigned threads, 
   }
 }
 
+// Stable counting sort of the items 0..n-1 by key(i) in [0, numKeys): out[...] = item indices grouped by key, ascending
+// inside a group; begin[k] = first position of key k.  The item range is cut into one slice per thread, every slice
+// counts and scatters on its own.
+template <class KeyFn>
+void groupByKey(const int64_t n, const int numKeys, unsigned threads, KeyFn&& key, std::vector<int64_t>& begin,
+                std::vector<int64_t>& out)
+{
+  if (threads == 0) {
+    threads = std::max(1u, std::thread::hardware_concurrency());
+  }
+  const int T = static_cast<int>(std::max<int64_t>(1, std::min<int64_t>(threads, n / (1 << 16) + 1)));
+  std::vector<std::vector<int64_t>> hist(static_cast<size_t>(T), std::vector<int64_t>(static_cast<size_t>(numKeys), 0));
+  auto slice = [&](const int t) { return std::make_pair(n * t / T, n * (t + 1) / T); };
+  auto run = [&](auto&& body) {
+    std::vector<std::thread> pool;
+    for (int t = 1; t < T; ++t) {
+      pool.emplace_back(body, t);
+    }
+    body(0);
+    for (auto& th : pool) {
+      th.join();
+    }
+  };
+  run([&](const int t) {
+    const auto [lo, hi] = slice(t);
+    for (int64_t i = lo; i < hi; ++i) {
+      ++hist[static_cast<size_t>(t)][static_cast<size_t>(key(i))];
+    }
+  });
+  begin.assign(static_cast<size_t>(numKeys) + 1, 0);
+  int64_t runTotal = 0;
+  for (int k = 0; k < numKeys; ++k) {
+    begin[static_cast<size_t>(k)] = runTotal;
+    for (int t = 0; t < T; ++t) {
+      const int64_t c = hist[static_cast<size_t>(t)][static_cast<size_t>(k)];
+      hist[static_cast<size_t>(t)][static_cast<size_t>(k)] = runTotal;  // now: where slice t writes its first item of key k
+      runTotal += c;
+    }
+  }
+  begin[static_cast<size_t>(numKeys)] = runTotal;
+  out.resize(static_cast<size_t>(n));
+  run([&](const int t) {
+    const auto [lo, hi] = slice(t);
+    std::vector<int64_t>& cursor = hist[static_cast<size_t>(t)];
+    for (int64_t i = lo; i < hi; ++i) {
+      out[static_cast<size_t>(cursor[static_cast<size_t>(key(i))]++)] = i;
+    }
+  });
+}
+
 template <class WordFn, class LengthFn, class EmitFn>
 void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const uint32_t numHaps, const int numWords,
                               const int gap, WordFn&& rawWord, LengthFn&& longEnough, EmitFn&& emit,
@@ -333,25 +386,21 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   if (numWords <= 0) {
     return;
   }
-  // ---- intervals grouped by start word and by end word (counting sorts) ------------------------------------
-  std::vector<int64_t> startBegin(static_cast<size_t>(numWords) + 1, 0), endBegin(static_cast<size_t>(numWords) + 1, 0);
-  for (int64_t i = 0; i < n; ++i) {
-    ++startBegin[static_cast<size_t>(intervals[i].startWord) + 1];
-    ++endBegin[static_cast<size_t>(intervals[i].endWord) + 1];
-  }
-  for (int w = 0; w < numWords; ++w) {
-    startBegin[w + 1] += startBegin[w];
-    endBegin[w + 1] += endBegin[w];
-  }
-  std::vector<int64_t> byStart(static_cast<size_t>(n)), byEnd(static_cast<size_t>(n));
-  {
-    std::vector<int64_t> cs(startBegin.begin(), startBegin.end() - 1), ce(endBegin.begin(), endBegin.end() - 1);
-    for (int64_t i = 0; i < n; ++i) {
-      byStart[static_cast<size_t>(cs[intervals[i].startWord]++)] = i;
-      byEnd[static_cast<size_t>(ce[intervals[i].endWord]++)] = i;
+  const bool trace = std::getenv("FSMC_TRACE") != nullptr;  // development: host time of the phases
+  auto clock = [] { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
+  double tPhase = clock();
+  auto lap = [&](const char* what) {
+    if (trace) {
+      const double t = clock();
+      std::fprintf(stderr, "replayReferenceOrderFast: %-28s %.3f s\n", what, t - tPhase);
+      tPhase = t;
     }
-  }
-
+  };
+  // ---- intervals grouped by start word ---------------------------------------------------------------------------
+  std::vector<int64_t> startBegin, endBegin, byStart;
+  groupByKey(n, numWords, threads, [&](const int64_t i) { return intervals[static_cast<size_t>(i)].startWord; }, startBegin,
+             byStart);
+  lap("group by start word");
   // ---- phase 1: creation order of each word's new intervals -----------------------------------------------------
   // bucket count of the seed map at the start of every word: it only grows, by the number of distinct keys
   std::vector<size_t> distinct(static_cast<size_t>(numWords), 0);
@@ -371,6 +420,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       buckets = NodeOrderMap::bucketsAfter(buckets, distinct[w]);
     }
   }
+  lap("seed-map bucket counts");
   parallelForWords(numWords, threads, [&](const int w) {
     const int64_t lo = startBegin[w], hi = startBegin[w + 1];
     if (lo == hi) {
@@ -408,105 +458,146 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       byStart[static_cast<size_t>(q)] = created[static_cast<size_t>(q - lo)].index;
     }
   });
-
+  lap("creation order per word");
+  // From here on an interval is named by its creation rank q (its position in byStart): everything the sequential
+  // phase touches is then laid out in the order it is visited.  byEnd lists the ranks by end word, ascending.
+  std::vector<fsmc_match> ordered(static_cast<size_t>(n));
+  parallelForWords(numWords, threads, [&](const int w) {
+    for (int64_t q = startBegin[w]; q < startBegin[w + 1]; ++q) {
+      ordered[static_cast<size_t>(q)] = intervals[static_cast<size_t>(byStart[static_cast<size_t>(q)])];
+    }
+  });
+  std::vector<int64_t> byEnd;
+  groupByKey(n, numWords, threads, [&](const int64_t q) { return ordered[static_cast<size_t>(q)].endWord; }, endBegin, byEnd);
+  lap("reorder, group by end word");
   // ---- phase 2: the extend map's node order as (G, W) keys ------------------------------------------------------
   std::vector<int64_t> nodeG(static_cast<size_t>(n)), nodeW(static_cast<size_t>(n));
   std::vector<uint32_t> nodeBucket(static_cast<size_t>(n));
   size_t buckets = 17, count = 0;
-  std::vector<int32_t> live(buckets, 0);
-  std::vector<int64_t> bucketG(buckets, 0);
-  int64_t tick = 1;
-  auto pairKey = [&](const int64_t i) {
-    return static_cast<uint64_t>(intervals[static_cast<size_t>(i)].hapA) * numHaps + intervals[static_cast<size_t>(i)].hapB;
+  struct BucketState {
+    int64_t G = 0;     // key of the bucket's group, valid while live > 0
+    int64_t live = 0;  // nodes of the bucket in the map
   };
+  std::vector<BucketState> bucket(buckets);
+  int64_t tick = 1;
+  constexpr int64_t kAhead = 24;  // software prefetch distance: the bucket table (tens of MB) is hit at random
+  auto pairKey = [&](const int64_t q) {
+    return static_cast<uint64_t>(ordered[static_cast<size_t>(q)].hapA) * numHaps + ordered[static_cast<size_t>(q)].hapB;
+  };
+  // key % buckets without a hardware divide: q = floor(key * ceil(2^64 / d) / 2^64) is the quotient or one more
+  uint64_t magic = 0;
+  auto setBuckets = [&](const size_t d) {
+    buckets = d;
+    magic = static_cast<uint64_t>((static_cast<unsigned __int128>(1) << 64) / d) + 1;
+  };
+  auto bucketOf = [&](const uint64_t key) {
+    const uint64_t quot = static_cast<uint64_t>((static_cast<unsigned __int128>(key) * magic) >> 64);
+    int64_t r = static_cast<int64_t>(key - quot * buckets);
+    if (r < 0) {
+      r += static_cast<int64_t>(buckets);
+    }
+    return static_cast<size_t>(r);
+  };
+  setBuckets(17);
   auto byListOrder = [&](const int64_t x, const int64_t y) {
     return nodeG[static_cast<size_t>(x)] != nodeG[static_cast<size_t>(y)] ? nodeG[static_cast<size_t>(x)] < nodeG[static_cast<size_t>(y)]
                                                                            : nodeW[static_cast<size_t>(x)] < nodeW[static_cast<size_t>(y)];
   };
   std::vector<int64_t> scratch;
-  // nodes alive while word w's intervals are being inserted: inserted so far, end word >= w - gap - 1
-  auto rehash = [&](const size_t newBuckets, const int w, const int64_t insertedOfW) {
+  // nodes alive while word w's intervals are being inserted: created so far (rank < upTo), end word >= w - gap - 1
+  auto rehash = [&](const size_t newBuckets, const int w, const int64_t upTo) {
     scratch.clear();
     const int minEnd = w - gap - 1;
-    for (int v = 0; v <= w; ++v) {
-      const int64_t hi = v < w ? startBegin[v + 1] : startBegin[v] + insertedOfW;
-      for (int64_t q = startBegin[v]; q < hi; ++q) {
-        const int64_t i = byStart[static_cast<size_t>(q)];
-        if (intervals[static_cast<size_t>(i)].endWord >= minEnd) {
-          scratch.push_back(i);
-        }
+    for (int64_t q = 0; q < upTo; ++q) {
+      if (ordered[static_cast<size_t>(q)].endWord >= minEnd) {
+        scratch.push_back(q);
       }
     }
     std::sort(scratch.begin(), scratch.end(), byListOrder);
-    buckets = newBuckets;
-    live.assign(buckets, 0);
-    bucketG.assign(buckets, 0);
+    setBuckets(newBuckets);
+    bucket.assign(buckets, BucketState{});
     const int64_t N = static_cast<int64_t>(scratch.size());
     for (int64_t e = 0; e < N; ++e) {
-      const int64_t i = scratch[static_cast<size_t>(e)];
-      const size_t b = static_cast<size_t>(pairKey(i) % buckets);
-      if (live[b] == 0) {
-        bucketG[b] = -(tick + N - e);  // groups in the order their first node is met
+      const int64_t q = scratch[static_cast<size_t>(e)];
+      const size_t b = bucketOf(pairKey(q));
+      if (bucket[b].live == 0) {
+        bucket[b].G = -(tick + N - e);  // groups in the order their first node is met
       }
-      ++live[b];
-      nodeBucket[static_cast<size_t>(i)] = static_cast<uint32_t>(b);
-      nodeG[static_cast<size_t>(i)] = bucketG[b];
-      nodeW[static_cast<size_t>(i)] = -(tick + e);  // inside a group: reverse order of the walk
+      ++bucket[b].live;
+      nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
+      nodeG[static_cast<size_t>(q)] = bucket[b].G;
+      nodeW[static_cast<size_t>(q)] = -(tick + e);  // inside a group: reverse order of the walk
     }
     tick += N + 1;
   };
-  auto flushSet = [&](std::vector<int64_t>& leaving) {
+  std::vector<int64_t> leaving;
+  auto flushSet = [&] {
     std::sort(leaving.begin(), leaving.end(), byListOrder);
-    for (const int64_t i : leaving) {
-      emit(i);
+    for (const int64_t q : leaving) {
+      emit(byStart[static_cast<size_t>(q)]);
     }
     leaving.clear();
   };
-  std::vector<int64_t> leaving;
+  double tIns = 0, tErase = 0, tFlush = 0;
   for (int w = 0; w < numWords; ++w) {
+    const double c0 = trace ? clock() : 0;
     for (int64_t q = startBegin[w]; q < startBegin[w + 1]; ++q) {
-      const int64_t i = byStart[static_cast<size_t>(q)];
       if (count + 1 > buckets) {  // max load factor 1.0
         const size_t want = NodeOrderMap::growTo(count);
         if (want != buckets) {
-          rehash(want, w, q - startBegin[w]);
+          rehash(want, w, q);
         }
       }
-      const size_t b = static_cast<size_t>(pairKey(i) % buckets);
-      if (live[b] == 0) {
-        bucketG[b] = -tick;  // a new group goes to the front of the list
+      if (q + kAhead < n) {
+        __builtin_prefetch(&bucket[bucketOf(pairKey(q + kAhead))], 1);
       }
-      ++live[b];
+      const size_t b = bucketOf(pairKey(q));
+      if (bucket[b].live == 0) {
+        bucket[b].G = -tick;  // a new group goes to the front of the list
+      }
+      ++bucket[b].live;
       ++count;
-      nodeBucket[static_cast<size_t>(i)] = static_cast<uint32_t>(b);
-      nodeG[static_cast<size_t>(i)] = bucketG[b];
-      nodeW[static_cast<size_t>(i)] = -tick;  // front of its group
+      nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
+      nodeG[static_cast<size_t>(q)] = bucket[b].G;
+      nodeW[static_cast<size_t>(q)] = -tick;  // front of its group
       ++tick;
     }
+    const double c1 = trace ? clock() : 0;
+    tIns += c1 - c0;
     // ExtendHash::clearPairsPriorTo(w - gap): exactly the intervals that ended at word w - gap - 1 leave now
     const int e = w - gap - 1;
     if (e >= 0) {
-      for (int64_t q = endBegin[e]; q < endBegin[e + 1]; ++q) {
-        const int64_t i = byEnd[static_cast<size_t>(q)];
-        --live[nodeBucket[static_cast<size_t>(i)]];
+      for (int64_t k = endBegin[e]; k < endBegin[e + 1]; ++k) {
+        const int64_t q = byEnd[static_cast<size_t>(k)];
+        if (k + kAhead < endBegin[e + 1]) {
+          __builtin_prefetch(&bucket[nodeBucket[static_cast<size_t>(byEnd[static_cast<size_t>(k + kAhead)])]], 1);
+        }
+        --bucket[nodeBucket[static_cast<size_t>(q)]].live;
         --count;
-        if (longEnough(intervals[static_cast<size_t>(i)])) {
-          leaving.push_back(i);
+        if (longEnough(ordered[static_cast<size_t>(q)])) {
+          leaving.push_back(q);
         }
       }
-      flushSet(leaving);
+      const double c2 = trace ? clock() : 0;
+      tErase += c2 - c1;
+      flushSet();
+      tFlush += trace ? clock() - c2 : 0;
     }
+  }
+  if (trace) {
+    std::fprintf(stderr, "replayReferenceOrderFast:   inserts %.3f s, erases %.3f s, sorted emission %.3f s\n", tIns, tErase, tFlush);
   }
   // ExtendHash::clearAllPairs: everything still in the map, in list order
   for (int e = std::max(0, numWords - gap - 1); e < numWords; ++e) {
-    for (int64_t q = endBegin[e]; q < endBegin[e + 1]; ++q) {
-      const int64_t i = byEnd[static_cast<size_t>(q)];
-      if (longEnough(intervals[static_cast<size_t>(i)])) {
-        leaving.push_back(i);
+    for (int64_t k = endBegin[e]; k < endBegin[e + 1]; ++k) {
+      const int64_t q = byEnd[static_cast<size_t>(k)];
+      if (longEnough(ordered[static_cast<size_t>(q)])) {
+        leaving.push_back(q);
       }
     }
   }
-  flushSet(leaving);
+  flushSet();
+  lap("node keys, flushes, emission");
 }
 
 }  // namespace candidate_order
