@@ -2,7 +2,9 @@
 // Host side of the decode path: device buffers, model assembly, tile scheduling, launches.
 #include <algorithm>
 #include <atomic>
+#include <chrono>
 #include <cstdarg>
+#include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -14,6 +16,7 @@
 #include "decode_kernels.cuh"
 #include "decode_fast.cuh"
 #include "seed_kernels.cuh"
+#include "segment_sort.h"
 #include "split_select.h"
 
 namespace
@@ -137,6 +140,7 @@ struct fsmc_ctx {
   // host staging of segment records and the per-pair counters of their counting sort (fsmc_plan_collect)
   PinnedBuf<fsmc_segment> segStage;
   std::vector<uint32_t> pairOffset, pairFirst;
+  fsmc::SegmentSorter segmentSorter;  // device-side ordering of the records (segment_sort.h)
   // a destroyed plan is parked here so that the next fsmc_plan_create reuses its device buffers (fsmc_decode makes
   // one plan per call; cudaMalloc/cudaFree per call would serialise the device)
   fsmc_plan* sparePlan = nullptr;
@@ -767,9 +771,12 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
       if (!out->segments || out->segmentCapacity < stored) {
         return fail(FSMC_E_INVALID, "fsmc_plan_collect: segment buffer missing or smaller than at plan creation");
       }
+      // reference order = ascending (pair, first site): stable sort by pair on the device (a lane appends its
+      // segments in ascending site order), then one copy into pinned staging
+      const fsmc_segment* sorted = nullptr;
+      FSMC_CUDA(ctx->segmentSorter.sort(plan->segments.p, stored, static_cast<uint32_t>(plan->numTiles * 32), st, &sorted));
       FSMC_CUDA(ctx->segStage.ensure(static_cast<size_t>(stored)));
-      FSMC_CUDA(cudaMemcpyAsync(ctx->segStage.p, plan->segments.p, stored * sizeof(fsmc_segment), cudaMemcpyDeviceToHost,
-                                st));
+      FSMC_CUDA(cudaMemcpyAsync(ctx->segStage.p, sorted, stored * sizeof(fsmc_segment), cudaMemcpyDeviceToHost, st));
     }
   }
   const size_t nSite = static_cast<size_t>(plan->numTiles) * 32 * static_cast<size_t>(plan->siteStride);
@@ -808,36 +815,23 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
   FSMC_CUDA(cudaEventRecord(ctx->ev[3], st));
   FSMC_CUDA(cudaStreamSynchronize(st));
   if (stored > 0) {
-    // reference order: batches in submission order, pairs in batch order, sites ascending.  A lane appends its
-    // segments in ascending site order, so a stable counting sort by pair from the staging buffer into the caller's
-    // buffer restores it in O(n); the insertion pass is a guard that never moves anything in practice.
+    // the records arrive sorted by pair (device radix sort); copy them out and check the order, sites included
     const fsmc_segment* in = ctx->segStage.p;
-    std::vector<uint32_t>& off = ctx->pairOffset;
     const size_t nPairs = static_cast<size_t>(plan->numTiles) * 32;
-    off.assign(nPairs + 1, 0u);
+    std::memcpy(out->segments, in, static_cast<size_t>(stored) * sizeof(fsmc_segment));
+    bool ordered = true;
     for (long long i = 0; i < stored; ++i) {
       if (in[i].pair >= nPairs) {
         return fail(FSMC_E_CUDA, "fsmc_plan_collect: corrupt segment record (pair %u of %zu)", in[i].pair, nPairs);
       }
-      ++off[in[i].pair + 1];
-    }
-    for (size_t q = 0; q < nPairs; ++q) {
-      off[q + 1] += off[q];
-    }
-    // After the scan off[q] is the first slot of pair q; it then advances as the pair's records arrive.  The guard only
-    // looks at slots of the SAME pair that are already filled: the slot before them belongs to another pair and may
-    // still hold whatever the caller's buffer contained before the call.
-    std::vector<uint32_t>& first = ctx->pairFirst;
-    first.assign(off.begin(), off.end() - 1);
-    for (long long i = 0; i < stored; ++i) {
-      const uint32_t q = in[i].pair;
-      fsmc_segment* const lo = out->segments + first[q];
-      fsmc_segment* dst = out->segments + off[q]++;
-      *dst = in[i];
-      while (dst > lo && dst[-1].posStart > dst->posStart) {
-        std::swap(dst[-1], dst[0]);
-        --dst;
+      if (i > 0 && (in[i - 1].pair > in[i].pair || (in[i - 1].pair == in[i].pair && in[i - 1].posStart > in[i].posStart))) {
+        ordered = false;
       }
+    }
+    if (!ordered) {  // never taken by the kernels of this library (one lane emits a pair's segments in site order)
+      std::stable_sort(out->segments, out->segments + stored, [](const fsmc_segment& x, const fsmc_segment& y) {
+        return x.pair != y.pair ? x.pair < y.pair : x.posStart < y.posStart;
+      });
     }
   }
   if (found > plan->segmentCapacity) {

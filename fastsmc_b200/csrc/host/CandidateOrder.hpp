@@ -20,9 +20,12 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <new>
 #include <thread>
 #include <utility>
 #include <vector>
+
+#include <sys/mman.h>
 
 #include "../../../include/fastsmc_b200.h"
 
@@ -327,6 +330,42 @@ template <class Fn> void parallelForWords(const int numWords, unsigned threads, 
   }
 }
 
+// Zero-filled array for a table that is hit at random: backed by transparent huge pages where the system allows it
+// (a 25 MB table on 4 KB pages misses the TLB on nearly every access, and page walks are slow under virtualisation).
+template <class T> class HugeArray
+{
+public:
+  explicit HugeArray(const size_t count) { reset(count); }
+  HugeArray(const HugeArray&) = delete;
+  HugeArray& operator=(const HugeArray&) = delete;
+  ~HugeArray() { release(); }
+  void reset(const size_t count)
+  {
+    release();
+    constexpr size_t kHuge = size_t{2} << 20;
+    mBytes = (std::max<size_t>(count, 1) * sizeof(T) + kHuge - 1) / kHuge * kHuge;
+    void* p = mmap(nullptr, mBytes, PROT_READ | PROT_WRITE, MAP_PRIVATE | MAP_ANONYMOUS, -1, 0);
+    if (p == MAP_FAILED) {
+      throw std::bad_alloc();
+    }
+    madvise(p, mBytes, MADV_HUGEPAGE);  // advisory; anonymous mappings are zero-filled either way
+    mData = static_cast<T*>(p);
+  }
+  T& operator[](const size_t i) { return mData[i]; }
+  const T& operator[](const size_t i) const { return mData[i]; }
+
+private:
+  void release()
+  {
+    if (mData) {
+      munmap(mData, mBytes);
+      mData = nullptr;
+    }
+  }
+  T* mData = nullptr;
+  size_t mBytes = 0;
+};
+
 // Stable counting sort of the items 0..n-1 by key(i) in [0, numKeys): out[...] = item indices grouped by key, ascending
 // inside a group; begin[k] = first position of key k.  The item range is cut into one slice per thread, every slice
 // counts and scatters on its own.
@@ -426,18 +465,18 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     if (lo == hi) {
       return;
     }
+    // node of every haplotype's word in the seed map, then the node's place in the map's iteration order
     NodeOrderMap seeds(seedBuckets[w]);
+    std::vector<int> nodeOfHap(numHaps);
     for (uint32_t h = 0; h < numHaps; ++h) {
       bool isNew;
-      seeds.insert(rawWord(h, w), 0, isNew);
+      nodeOfHap[h] = seeds.insert(rawWord(h, w), 0, isNew);
     }
-    std::vector<std::pair<uint64_t, int64_t>> rank;
-    rank.reserve(seeds.size());
+    std::vector<int64_t> rankOfNode(numHaps, 0);
     int64_t r = 0;
     for (int nd = seeds.first(); nd != NodeOrderMap::kEnd; nd = seeds.next(nd)) {
-      rank.emplace_back(seeds.key(nd), r++);
+      rankOfNode[static_cast<size_t>(nd)] = r++;
     }
-    std::sort(rank.begin(), rank.end());
     struct Creation {
       int64_t rank;
       uint32_t a, b;
@@ -448,8 +487,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     for (int64_t q = lo; q < hi; ++q) {
       const int64_t i = byStart[static_cast<size_t>(q)];
       const fsmc_match& m = intervals[static_cast<size_t>(i)];
-      const auto it = std::lower_bound(rank.begin(), rank.end(), std::make_pair(rawWord(m.hapA, w), int64_t{0}));
-      created.push_back(Creation{it->second, m.hapA, m.hapB, i});
+      created.push_back(Creation{rankOfNode[static_cast<size_t>(nodeOfHap[m.hapA])], m.hapA, m.hapB, i});
     }
     std::sort(created.begin(), created.end(), [](const Creation& x, const Creation& y) {
       return x.rank != y.rank ? x.rank < y.rank : (x.a != y.a ? x.a < y.a : x.b < y.b);
@@ -471,20 +509,22 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   groupByKey(n, numWords, threads, [&](const int64_t q) { return ordered[static_cast<size_t>(q)].endWord; }, endBegin, byEnd);
   lap("reorder, group by end word");
   // ---- phase 2: the extend map's node order as (G, W) keys ------------------------------------------------------
-  std::vector<int64_t> nodeG(static_cast<size_t>(n)), nodeW(static_cast<size_t>(n));
+  // G lives in the bucket table (valid while the bucket is non-empty, so it can be read whenever one of the bucket's
+  // nodes is still in the map); W and the bucket index are kept per node.
+  std::vector<int64_t> nodeW(static_cast<size_t>(n));
   std::vector<uint32_t> nodeBucket(static_cast<size_t>(n));
-  size_t buckets = 17, count = 0;
   struct BucketState {
-    int64_t G = 0;     // key of the bucket's group, valid while live > 0
-    int64_t live = 0;  // nodes of the bucket in the map
+    int64_t G;     // key of the bucket's group, valid while live > 0
+    int64_t live;  // nodes of the bucket in the map
   };
-  std::vector<BucketState> bucket(buckets);
+  size_t buckets = 17, count = 0;
+  HugeArray<BucketState> bucket(buckets);
   int64_t tick = 1;
   constexpr int64_t kAhead = 24;  // software prefetch distance: the bucket table (tens of MB) is hit at random
   auto pairKey = [&](const int64_t q) {
     return static_cast<uint64_t>(ordered[static_cast<size_t>(q)].hapA) * numHaps + ordered[static_cast<size_t>(q)].hapB;
   };
-  // key % buckets without a hardware divide: q = floor(key * ceil(2^64 / d) / 2^64) is the quotient or one more
+  // key % buckets without a hardware divide: floor(key * ceil(2^64 / d) / 2^64) is the quotient or one more
   uint64_t magic = 0;
   auto setBuckets = [&](const size_t d) {
     buckets = d;
@@ -499,42 +539,44 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     return static_cast<size_t>(r);
   };
   setBuckets(17);
-  auto byListOrder = [&](const int64_t x, const int64_t y) {
-    return nodeG[static_cast<size_t>(x)] != nodeG[static_cast<size_t>(y)] ? nodeG[static_cast<size_t>(x)] < nodeG[static_cast<size_t>(y)]
-                                                                           : nodeW[static_cast<size_t>(x)] < nodeW[static_cast<size_t>(y)];
+  struct Placed {
+    int64_t G, W, q;
+    bool operator<(const Placed& o) const { return G != o.G ? G < o.G : W < o.W; }
   };
-  std::vector<int64_t> scratch;
+  auto placeOf = [&](const int64_t q) {
+    return Placed{bucket[nodeBucket[static_cast<size_t>(q)]].G, nodeW[static_cast<size_t>(q)], q};
+  };
+  std::vector<Placed> scratch;
   // nodes alive while word w's intervals are being inserted: created so far (rank < upTo), end word >= w - gap - 1
   auto rehash = [&](const size_t newBuckets, const int w, const int64_t upTo) {
     scratch.clear();
     const int minEnd = w - gap - 1;
     for (int64_t q = 0; q < upTo; ++q) {
       if (ordered[static_cast<size_t>(q)].endWord >= minEnd) {
-        scratch.push_back(q);
+        scratch.push_back(placeOf(q));
       }
     }
-    std::sort(scratch.begin(), scratch.end(), byListOrder);
+    std::sort(scratch.begin(), scratch.end());
     setBuckets(newBuckets);
-    bucket.assign(buckets, BucketState{});
+    bucket.reset(buckets);
     const int64_t N = static_cast<int64_t>(scratch.size());
     for (int64_t e = 0; e < N; ++e) {
-      const int64_t q = scratch[static_cast<size_t>(e)];
+      const int64_t q = scratch[static_cast<size_t>(e)].q;
       const size_t b = bucketOf(pairKey(q));
       if (bucket[b].live == 0) {
         bucket[b].G = -(tick + N - e);  // groups in the order their first node is met
       }
       ++bucket[b].live;
       nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
-      nodeG[static_cast<size_t>(q)] = bucket[b].G;
       nodeW[static_cast<size_t>(q)] = -(tick + e);  // inside a group: reverse order of the walk
     }
     tick += N + 1;
   };
-  std::vector<int64_t> leaving;
+  std::vector<Placed> leaving;
   auto flushSet = [&] {
-    std::sort(leaving.begin(), leaving.end(), byListOrder);
-    for (const int64_t q : leaving) {
-      emit(byStart[static_cast<size_t>(q)]);
+    std::sort(leaving.begin(), leaving.end());
+    for (const Placed& p : leaving) {
+      emit(byStart[static_cast<size_t>(p.q)]);
     }
     leaving.clear();
   };
@@ -552,13 +594,12 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
         __builtin_prefetch(&bucket[bucketOf(pairKey(q + kAhead))], 1);
       }
       const size_t b = bucketOf(pairKey(q));
-      if (bucket[b].live == 0) {
-        bucket[b].G = -tick;  // a new group goes to the front of the list
+      BucketState& st = bucket[b];
+      if (st.live++ == 0) {
+        st.G = -tick;  // a new group goes to the front of the list
       }
-      ++bucket[b].live;
       ++count;
       nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
-      nodeG[static_cast<size_t>(q)] = bucket[b].G;
       nodeW[static_cast<size_t>(q)] = -tick;  // front of its group
       ++tick;
     }
@@ -572,11 +613,12 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
         if (k + kAhead < endBegin[e + 1]) {
           __builtin_prefetch(&bucket[nodeBucket[static_cast<size_t>(byEnd[static_cast<size_t>(k + kAhead)])]], 1);
         }
-        --bucket[nodeBucket[static_cast<size_t>(q)]].live;
-        --count;
+        BucketState& st = bucket[nodeBucket[static_cast<size_t>(q)]];
         if (longEnough(ordered[static_cast<size_t>(q)])) {
-          leaving.push_back(q);
+          leaving.push_back(Placed{st.G, nodeW[static_cast<size_t>(q)], q});  // G stays readable until the next insert
         }
+        --st.live;
+        --count;
       }
       const double c2 = trace ? clock() : 0;
       tErase += c2 - c1;
@@ -592,7 +634,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     for (int64_t k = endBegin[e]; k < endBegin[e + 1]; ++k) {
       const int64_t q = byEnd[static_cast<size_t>(k)];
       if (longEnough(ordered[static_cast<size_t>(q)])) {
-        leaving.push_back(q);
+        leaving.push_back(placeOf(q));
       }
     }
   }
