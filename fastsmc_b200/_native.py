@@ -232,7 +232,9 @@ class Context:
     def _request(self, tiles, flags, segment_capacity, site_stride, segment_prefill=None):
         T = len(tiles["tilePairs"])
         out = {}
-        seg = np.zeros(max(segment_capacity, 1), SEGMENT_DTYPE) if flags & CALL_SEGMENTS else None
+        # uninitialised on purpose: the library never reads the caller's record buffer, and zero-filling capacity-sized
+        # buffers would be host time inside every call
+        seg = np.empty(max(segment_capacity, 1), SEGMENT_DTYPE) if flags & CALL_SEGMENTS else None
         if seg is not None and segment_prefill is not None:
             # previous contents of the caller's record buffer (the library must not depend on them)
             n = min(len(seg), len(segment_prefill))

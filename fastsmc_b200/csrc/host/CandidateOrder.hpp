@@ -20,6 +20,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <new>
 #include <thread>
 #include <utility>
@@ -330,6 +331,41 @@ template <class Fn> void parallelForWords(const int numWords, unsigned threads, 
   }
 }
 
+// Sort on all host threads: equal slices sorted concurrently, then rounds of pairwise in-place merges.
+template <class T, class Less> void parallelSort(std::vector<T>& v, Less less, unsigned threads = 0)
+{
+  if (threads == 0) {
+    threads = std::max(1u, std::thread::hardware_concurrency());
+  }
+  const size_t n = v.size();
+  size_t parts = 1;
+  while (parts * 2 <= threads && n / (parts * 2) >= (size_t{1} << 16)) {
+    parts *= 2;
+  }
+  if (parts == 1) {
+    std::sort(v.begin(), v.end(), less);
+    return;
+  }
+  auto bound = [&](const size_t i) { return n * i / parts; };
+  auto runAll = [&](const size_t jobs, auto&& body) {
+    std::vector<std::thread> pool;
+    for (size_t j = 1; j < jobs; ++j) {
+      pool.emplace_back(body, j);
+    }
+    body(size_t{0});
+    for (auto& th : pool) {
+      th.join();
+    }
+  };
+  runAll(parts, [&](const size_t j) { std::sort(v.begin() + bound(j), v.begin() + bound(j + 1), less); });
+  for (size_t width = 1; width < parts; width *= 2) {
+    runAll(parts / (2 * width), [&](const size_t j) {
+      const size_t lo = bound(2 * width * j), mid = bound(2 * width * j + width), hi = bound(2 * width * (j + 1));
+      std::inplace_merge(v.begin() + lo, v.begin() + mid, v.begin() + hi, less);
+    });
+  }
+}
+
 // Zero-filled array for a table that is hit at random: backed by transparent huge pages where the system allows it
 // (a 25 MB table on 4 KB pages misses the TLB on nearly every access, and page walks are slow under virtualisation).
 template <class T> class HugeArray
@@ -439,6 +475,20 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   std::vector<int64_t> startBegin, endBegin, byStart;
   groupByKey(n, numWords, threads, [&](const int64_t i) { return intervals[static_cast<size_t>(i)].startWord; }, startBegin,
              byStart);
+  if (trace) {
+    long long sumLen = 0, longOnes = 0, maxLen = 0;
+    for (int64_t i = 0; i < n; ++i) {
+      const long long len = intervals[static_cast<size_t>(i)].endWord - intervals[static_cast<size_t>(i)].startWord + 1;
+      sumLen += len;
+      longOnes += len > 50;
+      maxLen = std::max(maxLen, len);
+    }
+    std::fprintf(stderr, "replayReferenceOrderFast: %lld intervals, mean length %.2f words, %lld longer than 50 words, longest %lld; "
+                 "starts in word 0: %lld, in word %d: %lld\n",
+                 static_cast<long long>(n), n ? static_cast<double>(sumLen) / n : 0.0, longOnes, maxLen,
+                 static_cast<long long>(startBegin[1] - startBegin[0]), numWords / 2,
+                 static_cast<long long>(startBegin[numWords / 2 + 1] - startBegin[numWords / 2]));
+  }
   lap("group by start word");
   // ---- phase 1: creation order of each word's new intervals -----------------------------------------------------
   // bucket count of the seed map at the start of every word: it only grows, by the number of distinct keys
@@ -460,9 +510,15 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     }
   }
   lap("seed-map bucket counts");
-  parallelForWords(numWords, threads, [&](const int w) {
+  // A low-complexity word (a stretch of rare SNPs where most haplotypes are identical) starts millions of intervals
+  // at once: such words are taken one at a time with the sort itself on all threads, the others one word per thread.
+  int64_t kBigWord = int64_t{1} << 21;
+  if (const char* e = std::getenv("FSMC_BIG_WORD")) {  // tests: exercise the whole-machine path on small data
+    kBigWord = std::max<int64_t>(1, std::atoll(e));
+  }
+  auto creationOrderOfWord = [&](const int w, const bool wholeMachine) {
     const int64_t lo = startBegin[w], hi = startBegin[w + 1];
-    if (lo == hi) {
+    if (lo == hi || ((hi - lo >= kBigWord) != wholeMachine)) {
       return;
     }
     // node of every haplotype's word in the seed map, then the node's place in the map's iteration order
@@ -489,13 +545,22 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       const fsmc_match& m = intervals[static_cast<size_t>(i)];
       created.push_back(Creation{rankOfNode[static_cast<size_t>(nodeOfHap[m.hapA])], m.hapA, m.hapB, i});
     }
-    std::sort(created.begin(), created.end(), [](const Creation& x, const Creation& y) {
+    auto less = [](const Creation& x, const Creation& y) {
       return x.rank != y.rank ? x.rank < y.rank : (x.a != y.a ? x.a < y.a : x.b < y.b);
-    });
+    };
+    if (wholeMachine) {
+      parallelSort(created, less, threads);
+    } else {
+      std::sort(created.begin(), created.end(), less);
+    }
     for (int64_t q = lo; q < hi; ++q) {
       byStart[static_cast<size_t>(q)] = created[static_cast<size_t>(q - lo)].index;
     }
-  });
+  };
+  parallelForWords(numWords, threads, [&](const int w) { creationOrderOfWord(w, false); });
+  for (int w = 0; w < numWords; ++w) {
+    creationOrderOfWord(w, true);
+  }
   lap("creation order per word");
   // From here on an interval is named by its creation rank q (its position in byStart): everything the sequential
   // phase touches is then laid out in the order it is visited.  byEnd lists the ranks by end word, ascending.
@@ -548,7 +613,13 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   };
   std::vector<Placed> scratch;
   // nodes alive while word w's intervals are being inserted: created so far (rank < upTo), end word >= w - gap - 1
+  double tRehash = 0;
+  int64_t numRehash = 0, rehashScanned = 0;
+  size_t maxLive = 0;
   auto rehash = [&](const size_t newBuckets, const int w, const int64_t upTo) {
+    const double r0 = trace ? clock() : 0;
+    ++numRehash;
+    rehashScanned += upTo;
     scratch.clear();
     const int minEnd = w - gap - 1;
     for (int64_t q = 0; q < upTo; ++q) {
@@ -556,7 +627,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
         scratch.push_back(placeOf(q));
       }
     }
-    std::sort(scratch.begin(), scratch.end());
+    parallelSort(scratch, std::less<Placed>(), threads);
     setBuckets(newBuckets);
     bucket.reset(buckets);
     const int64_t N = static_cast<int64_t>(scratch.size());
@@ -571,6 +642,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       nodeW[static_cast<size_t>(q)] = -(tick + e);  // inside a group: reverse order of the walk
     }
     tick += N + 1;
+    tRehash += trace ? clock() - r0 : 0;
   };
   std::vector<Placed> leaving;
   auto flushSet = [&] {
@@ -603,6 +675,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       nodeW[static_cast<size_t>(q)] = -tick;  // front of its group
       ++tick;
     }
+    maxLive = std::max(maxLive, count);
     const double c1 = trace ? clock() : 0;
     tIns += c1 - c0;
     // ExtendHash::clearPairsPriorTo(w - gap): exactly the intervals that ended at word w - gap - 1 leave now
@@ -627,7 +700,9 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     }
   }
   if (trace) {
-    std::fprintf(stderr, "replayReferenceOrderFast:   inserts %.3f s, erases %.3f s, sorted emission %.3f s\n", tIns, tErase, tFlush);
+    std::fprintf(stderr, "replayReferenceOrderFast:   inserts %.3f s (of which %lld rehashes over %lld nodes: %.3f s), erases %.3f s, "
+                 "sorted emission %.3f s; most nodes in the map %zu, buckets %zu\n",
+                 tIns, static_cast<long long>(numRehash), static_cast<long long>(rehashScanned), tRehash, tErase, tFlush, maxLive, buckets);
   }
   // ExtendHash::clearAllPairs: everything still in the map, in list order
   for (int e = std::max(0, numWords - gap - 1); e < numWords; ++e) {

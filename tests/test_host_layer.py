@@ -127,6 +127,12 @@ def test_fast_order_replay_equals_literal_replay_on_dense_matches(asmc, tmp_path
     slow = asmc.pyASMC.replayReferenceOrder(iv, d, gap, min_m, fast=False)
     fast = asmc.pyASMC.replayReferenceOrder(iv, d, gap, min_m, fast=True)
     assert len(slow) > 100 and list(slow) == list(fast)
+    # words that start very many intervals are sorted on all threads: same result when every word takes that path
+    os.environ["FSMC_BIG_WORD"] = "1"
+    try:
+        assert list(asmc.pyASMC.replayReferenceOrder(iv, d, gap, min_m, fast=True)) == list(slow)
+    finally:
+        del os.environ["FSMC_BIG_WORD"]
 
 
 def test_hmm_utils_known_answers(asmc):
