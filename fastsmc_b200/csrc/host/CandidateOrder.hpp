@@ -633,6 +633,9 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     const int64_t N = static_cast<int64_t>(scratch.size());
     for (int64_t e = 0; e < N; ++e) {
       const int64_t q = scratch[static_cast<size_t>(e)].q;
+      if (e + kAhead < N) {
+        __builtin_prefetch(&bucket[bucketOf(pairKey(scratch[static_cast<size_t>(e + kAhead)].q))], 1);
+      }
       const size_t b = bucketOf(pairKey(q));
       if (bucket[b].live == 0) {
         bucket[b].G = -(tick + N - e);  // groups in the order their first node is met
