@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 N_HAPS, N_SITES, SPAN_BP, CHROM, SEED = 1000, 10_000, 30_000_000, 1, 20201117 + 2
 DQ = os.path.join(ROOT, "data", "30-100-2000.decodingQuantities.gz")
 FLOPS_PER_PAIR_SITE_STATE = 35  # 15 forward + 15 backward + 3 combine + 2 consume
+NCU_DRAM_BYTES_PER_PAIR_SITE = (109.922461e9 + 109.458343e9) / (37888 * 10000)  # profiles/r1_v4_decodeFast_s69_ncu_full.txt
 WORKLOAD = "cfg2: all-pairs, hashing off, 1000 haplotypes x 10000 SNPs, S=69 (30-100-2000), time=50, batchSize=32"
 
 
@@ -337,7 +338,14 @@ def main():
                        "l2": f"no flush needed: each step streams {scratch_bytes / 2**30:.0f} GiB of backward-sweep scratch "
                              "through HBM (>> 126 MB L2)", "parallelism": f"{world} independent jobs, one per GPU"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak, "traffic": None, "peak_source": peak_src,
+                         "frac": achieved / hbm_peak,
+                         # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full
+                         # capture (profiles/r1_v4_decodeFast_s69_ncu_full.txt: 219.38 GB for 37 888 pairs x 10 000
+                         # sites = 579.0 B per pair-site, the padding of 69 states to 72 included), scaled to this
+                         # launch's pair-sites
+                         "traffic": NCU_DRAM_BYTES_PER_PAIR_SITE * pair_sites,
+                         "traffic_source": "ncu --set full capture of a 37888-pair launch, scaled by pair-sites",
+                         "algorithmic_bytes": bytes_per_pair_site * pair_sites, "peak_source": peak_src,
                          "kernel": "decodeFastKernel<69>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_pair_site": bytes_per_pair_site},
             "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,

@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <iostream>
 #include <numeric>
+#include <mutex>
 #include <random>
 #include <sstream>
 #include <stdexcept>
@@ -83,12 +84,9 @@ void Data::setJobGeometry(const DecodingParams& params)
   foldToMinorAlleles = params.foldData;
   decodingUsesCSFS = params.usingCSFS;
   mJobbing = (jobInd != -1) && (jobs != -1);
-  if (params.useKnownSeed) {
-    std::srand(1234u);
-  } else {
-    std::random_device rd;
-    std::srand(rd());
-  }
+  // ref: Data.cpp:55-61 seeds std::rand here; the only consumer is calculateUndistinguishedCounts, which seeds and draws
+  // under one lock, so that Data objects built on several host threads (one per GPU) do not share the sequence
+  mUseKnownSeed = params.useKnownSeed;
   if (mJobbing) {
     const double n = static_cast<double>(sampleSize);
     windowSize = static_cast<unsigned>(std::ceil(std::sqrt((2. * n * n - n) * 2. / jobs)));
@@ -518,6 +516,14 @@ std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int num
   };
   std::vector<Draw> draws;
   draws.reserve(static_cast<size_t>(sites) * 3);
+  static std::mutex randMutex;  // std::rand's state is process-wide
+  std::unique_lock<std::mutex> randLock(randMutex);
+  if (mUseKnownSeed) {
+    std::srand(1234u);
+  } else {
+    std::random_device rd;
+    std::srand(rd());
+  }
   for (int s = 0; s < sites; ++s) {
     const int total = totalSamplesCount[s];
     const int derived = derivedAlleleCounts[s];
@@ -536,6 +542,7 @@ std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int num
       }
     }
   }
+  randLock.unlock();
   std::atomic<size_t> next{0};
   auto work = [&] {
     std::vector<unsigned short> urn;

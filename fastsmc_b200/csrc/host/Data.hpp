@@ -34,6 +34,7 @@ public:
   int sites = 0;
   bool decodingUsesCSFS = false;
   bool mJobbing = false;
+  bool mUseKnownSeed = false;
   bool foldToMinorAlleles = false;
   std::vector<float> geneticPositions = {};
   std::vector<int> physicalPositions = {};

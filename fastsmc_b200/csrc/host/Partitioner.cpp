@@ -15,15 +15,6 @@
 namespace ASMC
 {
 
-namespace
-{
-std::mutex& modelPreparationMutex()
-{
-  static std::mutex m;
-  return m;
-}
-}  // namespace
-
 std::vector<int> jobOrder(const int jobs)
 {
   // job id -> (row w_i, position in row r): r even = below-diagonal full square, r odd = triangle (ref: Data.cpp:69-79)
@@ -74,11 +65,9 @@ std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vecto
         p.jobInd = order[i];
         p.device = device;
         p.verbose = false;
-        std::unique_ptr<FastSMC> job;
-        {
-          std::lock_guard<std::mutex> lock(modelPreparationMutex());
-          job = std::make_unique<FastSMC>(p);
-        }
+        // reading, model preparation and decoding of different jobs overlap freely: the only process-wide state, the
+        // std::rand sequence of the emission preparation, is seeded and consumed under its own lock (Data.cpp)
+        auto job = std::make_unique<FastSMC>(p);
         job->run();
         const HMM::RunStats& st = job->hmm().getRunStats();
         rep.candidates = job->getSeedingStats().candidates;
