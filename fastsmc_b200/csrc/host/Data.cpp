@@ -2,6 +2,7 @@
 #include "Data.hpp"
 
 #include <algorithm>
+#include <cstring>
 #include <thread>
 #include <atomic>
 #include <cmath>
@@ -137,6 +138,47 @@ Data::Data(const DecodingParams& params)
     readHapsAsmc(root);
     readMapAsmc(root);
   }
+}
+
+// Every job of a data set needs the same per-site information (allele counts are over the whole file) and the rows
+// of its own two sample windows; runAllJobs reads the files once and cuts the jobs out of the result.
+Data Data::forJob(const Data& whole, const DecodingParams& params)
+{
+  if (whole.numLoadedHaplotypes() != whole.haploidSampleSize) {
+    throw std::runtime_error("Data::forJob: the source must hold every sample of the data set");
+  }
+  Data d;
+  d.sampleSize = whole.sampleSize;
+  d.haploidSampleSize = whole.haploidSampleSize;
+  d.sites = whole.sites;
+  d.geneticPositions = whole.geneticPositions;
+  d.physicalPositions = whole.physicalPositions;
+  d.siteWasFlippedDuringFolding = whole.siteWasFlippedDuringFolding;
+  d.recRateAtMarker = whole.recRateAtMarker;
+  d.chrNumber = whole.chrNumber;
+  d.wordsPerHap = whole.wordsPerHap;
+  d.flipMask = whole.flipMask;
+  d.totalSamplesCount = whole.totalSamplesCount;
+  d.derivedAlleleCounts = whole.derivedAlleleCounts;
+  d.setJobGeometry(params);
+  if (d.foldToMinorAlleles != whole.foldToMinorAlleles) {
+    throw std::runtime_error("Data::forJob: folding differs between the source and the job");
+  }
+  for (unsigned n = 0; n < whole.sampleSize; ++n) {
+    if (d.readSample(n)) {
+      d.FamIDList.push_back(whole.FamIDList[n]);
+      d.IIDList.push_back(whole.IIDList[n]);
+      d.famAndIndNameList.push_back(whole.famAndIndNameList[n]);
+      d.globalHapId.push_back(2 * n);
+      d.globalHapId.push_back(2 * n + 1);
+    }
+  }
+  d.hapBits.resize(d.globalHapId.size() * static_cast<size_t>(d.wordsPerHap));
+  for (size_t l = 0; l < d.globalHapId.size(); ++l) {
+    std::memcpy(d.hapBits.data() + l * d.wordsPerHap, whole.hapBits.data() + static_cast<size_t>(d.globalHapId[l]) * d.wordsPerHap,
+                sizeof(uint64_t) * static_cast<size_t>(d.wordsPerHap));
+  }
+  return d;
 }
 
 void Data::allocate()

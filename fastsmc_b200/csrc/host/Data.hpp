@@ -72,6 +72,10 @@ public:
                          const std::vector<std::string>& iids, const uint8_t* rawAlleles, long numHaps, int numSites,
                          const std::vector<int>& physPos, const std::vector<double>& cM, int chr);
 
+  /// The Data of job params.jobInd of params.jobs, cut out of `whole` (a Data that loaded every sample, i.e. read
+  /// with jobs = jobInd = 1): the same object Data(params) would read from the files, without reading them again.
+  static Data forJob(const Data& whole, const DecodingParams& params);
+
   static int countHapLines(std::string inFileRoot);
   static int countSamplesLines(std::string inFileRoot);
 

@@ -2,6 +2,11 @@
 #include "HMM.hpp"
 
 #include <algorithm>
+#include <atomic>
+#include <thread>
+#include <mutex>
+#include <deque>
+#include <condition_variable>
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -99,13 +104,6 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
     m_flushPairs = static_cast<size_t>(m_batchSize) * static_cast<size_t>(std::max(1, std::atoi(e)));
   }
   uploadModel();
-}
-
-HMM::~HMM()
-{
-  if (m_ctx) {
-    fsmc_ctx_destroy(m_ctx);
-  }
 }
 
 // ref: HMM.cpp:504-513
@@ -233,6 +231,12 @@ HMM::ModelTables HMM::buildModelTables(const Data& data, const DecodingQuantitie
 
 void HMM::uploadModel()
 {
+  uploadModelTo(m_ctx);
+}
+
+void HMM::uploadModelTo(fsmc_ctx*& ctx)
+{
+  fsmc_ctx*& m_ctx = ctx;  // the body below fills whichever context it is given
   check(fsmc_ctx_create(decodingParams.device, &m_ctx), "fsmc_ctx_create");
   fsmc_model m{};
   m.states = m_model.states;
@@ -435,11 +439,13 @@ void HMM::decodeHapPairs(const std::vector<unsigned long>& hapsA, const std::vec
 void HMM::finishDecoding()
 {
   flushPending(true);
+  drainDecodes();
   m_observationsBatch.clear();
 }
 
 void HMM::closeIBDFile()
 {
+  drainDecodes();
   if (m_out) {
     const double t0 = now();
     m_out->writer.close();
@@ -451,6 +457,7 @@ void HMM::closeIBDFile()
 void HMM::finishFromHashing()
 {
   flushPending(true);
+  drainDecodes();
   closeIBDFile();
 }
 
@@ -525,9 +532,152 @@ TileSet buildTiles(const P* pend, const size_t n, const size_t batchSize, const 
 
 }  // namespace
 
+// ---------------------------------------------------------------------------------------------------------------
+// Segment decoding is pipelined: the caller's thread (candidate order replay, pair enumeration) only cuts chunks and
+// builds their tiles; decode workers, each with its own fsmc_ctx and stream, run fsmc_decode and hand the records to
+// the output pipeline.  With two workers the host side of one chunk (copies, record checks, formatting hand-over)
+// overlaps the kernel of the next.  Chunks complete strictly in submission order, so files and statistics are the
+// same as with one synchronous call per chunk.  Two contexts are only used when the request runs the narrow kernel:
+// the full-beta kernels size their scratch for the whole GPU.
+// ---------------------------------------------------------------------------------------------------------------
+struct HMM::ChunkJob {
+  size_t seq = 0;
+  TileSet tiles;
+  std::vector<Pending> pend;
+  std::shared_ptr<SegmentBlock> block;
+  fsmc_decode_stats st{};
+  double decodeWallS = 0.0;
+};
+
+struct HMM::DecodePipeline {
+  std::mutex mutex;
+  std::condition_variable cv;
+  std::deque<std::unique_ptr<ChunkJob>> queue;
+  size_t submitted = 0, completed = 0;
+  bool stop = false;
+  std::exception_ptr error;
+  std::vector<std::thread> workers;
+};
+
+HMM::~HMM()
+{
+  if (m_pipeline) {
+    {
+      std::unique_lock<std::mutex> lock(m_pipeline->mutex);
+      m_pipeline->cv.wait(lock, [&] { return m_pipeline->completed == m_pipeline->submitted; });
+      m_pipeline->stop = true;
+    }
+    m_pipeline->cv.notify_all();
+    for (auto& w : m_pipeline->workers) {
+      w.join();
+    }
+  }
+  if (m_ctx2) {
+    fsmc_ctx_destroy(m_ctx2);
+  }
+  if (m_ctx) {
+    fsmc_ctx_destroy(m_ctx);
+  }
+}
+
+void HMM::startDecodeWorkers()
+{
+  m_pipeline = std::make_unique<DecodePipeline>();
+  const bool ages = decodingParams.doPerPairPosteriorMean || decodingParams.doPerPairMAP;
+  const bool narrow = !decodingParams.exactArithmetic && (!ages || m_model.ageThreshold <= m_model.stateThreshold);
+  int workers = narrow ? 2 : 1;
+  if (const char* e = std::getenv("FSMC_DECODE_WORKERS")) {  // development / A-B runs
+    workers = std::max(1, std::min(2, std::atoi(e)));
+  }
+  if (workers == 2) {
+    uploadModelTo(m_ctx2);
+  }
+  for (int w = 0; w < workers; ++w) {
+    fsmc_ctx* ctx = w == 0 ? m_ctx : m_ctx2;
+    m_pipeline->workers.emplace_back([this, ctx] {
+      DecodePipeline& p = *m_pipeline;
+      for (;;) {
+        std::unique_ptr<ChunkJob> job;
+        {
+          std::unique_lock<std::mutex> lock(p.mutex);
+          p.cv.wait(lock, [&] { return p.stop || !p.queue.empty(); });
+          if (p.queue.empty()) {
+            return;
+          }
+          job = std::move(p.queue.front());
+          p.queue.pop_front();
+        }
+        std::exception_ptr err;
+        try {
+          decodeChunk(*job, ctx);
+        } catch (...) {
+          err = std::current_exception();
+        }
+        std::unique_lock<std::mutex> lock(p.mutex);
+        p.cv.wait(lock, [&] { return p.completed == job->seq; });  // chunks complete in submission order
+        if (!err && !p.error) {
+          lock.unlock();
+          try {
+            completeChunk(*job);
+          } catch (...) {
+            err = std::current_exception();
+          }
+          lock.lock();
+        }
+        if (err && !p.error) {
+          p.error = err;
+        }
+        ++p.completed;
+        lock.unlock();
+        p.cv.notify_all();
+      }
+    });
+  }
+}
+
+// Waits for every submitted chunk; rethrows the first error of a worker.
+void HMM::drainDecodes()
+{
+  if (!m_pipeline) {
+    return;
+  }
+  std::unique_lock<std::mutex> lock(m_pipeline->mutex);
+  m_pipeline->cv.wait(lock, [&] { return m_pipeline->completed == m_pipeline->submitted; });
+  if (m_pipeline->error) {
+    const std::exception_ptr e = m_pipeline->error;
+    m_pipeline->error = nullptr;
+    std::rethrow_exception(e);
+  }
+}
+
 void HMM::runSegmentChunk(const Pending* pend, const size_t n)
 {
-  TileSet t = buildTiles(pend, n, static_cast<size_t>(m_batchSize), m_windowed, data.geneticPositions, data.sites);
+  if (!m_pipeline) {
+    startDecodeWorkers();
+  }
+  auto job = std::make_unique<ChunkJob>();
+  job->tiles = buildTiles(pend, n, static_cast<size_t>(m_batchSize), m_windowed, data.geneticPositions, data.sites);
+  job->pend.assign(pend, pend + n);
+  DecodePipeline& p = *m_pipeline;
+  std::unique_lock<std::mutex> lock(p.mutex);
+  // at most one chunk waiting behind the ones being decoded: bounds memory, keeps every worker fed
+  p.cv.wait(lock, [&] { return p.submitted - p.completed <= p.workers.size() || p.error; });
+  if (p.error) {
+    const std::exception_ptr e = p.error;
+    p.error = nullptr;
+    std::rethrow_exception(e);
+  }
+  job->seq = p.submitted++;
+  p.queue.push_back(std::move(job));
+  lock.unlock();
+  p.cv.notify_all();
+}
+
+// Runs on a decode worker, any order.
+void HMM::decodeChunk(ChunkJob& job, fsmc_ctx* ctx)
+{
+  const TileSet& t = job.tiles;
+  const size_t n = job.pend.size();
   const bool ages = decodingParams.doPerPairPosteriorMean || decodingParams.doPerPairMAP;
   fsmc_decode_request req{};
   req.numTiles = static_cast<int64_t>(t.pairs.size());
@@ -540,24 +690,35 @@ void HMM::runSegmentChunk(const Pending* pend, const size_t n)
   req.tileScanTo = t.scanTo.data();
   req.flags = FSMC_CALL_SEGMENTS | (ages ? FSMC_SEG_AGE : 0u) | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u);
   // record buffer sized from the densest chunk seen so far (a retry after FSMC_E_OVERFLOW decodes the chunk again)
-  size_t capacity = std::max<size_t>(1024, static_cast<size_t>(static_cast<double>(n) * m_segmentsPerPair * 1.5) + 1024);
-  auto block = std::make_shared<SegmentBlock>();
-  fsmc_decode_stats st{};
+  size_t capacity =
+      std::max<size_t>(1024, static_cast<size_t>(static_cast<double>(n) * m_segmentsPerPair.load() * 1.5) + 1024);
+  job.block = std::make_shared<SegmentBlock>();
   for (;;) {
-    block->seg.reset(new fsmc_segment[capacity]);
-    req.segments = block->seg.get();
+    job.block->seg.reset(new fsmc_segment[capacity]);
+    req.segments = job.block->seg.get();
     req.segmentCapacity = static_cast<int64_t>(capacity);
     const double t0 = now();
-    const int rc = fsmc_decode(m_ctx, &req, &st);
-    m_stats.decodeWallS += now() - t0;
+    const int rc = fsmc_decode(ctx, &req, &job.st);
+    job.decodeWallS += now() - t0;
     if (rc == FSMC_E_OVERFLOW) {
-      capacity = static_cast<size_t>(st.numSegments) + 1024;
+      capacity = static_cast<size_t>(job.st.numSegments) + 1024;
       continue;
     }
     check(rc, "fsmc_decode");
     break;
   }
-  m_segmentsPerPair = std::max(m_segmentsPerPair, static_cast<double>(st.numSegments) / static_cast<double>(n));
+  const double perPair = static_cast<double>(job.st.numSegments) / static_cast<double>(n);
+  double seen = m_segmentsPerPair.load();
+  while (perPair > seen && !m_segmentsPerPair.compare_exchange_weak(seen, perPair)) {
+  }
+}
+
+// Runs on a decode worker, one chunk at a time, in submission order.
+void HMM::completeChunk(ChunkJob& job)
+{
+  const size_t n = job.pend.size();
+  const fsmc_decode_stats& st = job.st;
+  m_stats.decodeWallS += job.decodeWallS;
   m_stats.decodeCalls += 1;
   m_stats.pairsDecoded += n;
   m_stats.batches += (n + m_batchSize - 1) / m_batchSize;
@@ -569,9 +730,10 @@ void HMM::runSegmentChunk(const Pending* pend, const size_t n)
   const size_t count = static_cast<size_t>(st.numSegments);
   nbSegmentsDetected += count;
   m_stats.segments += count;
+  std::shared_ptr<SegmentBlock> block = job.block;
   block->count = count;
-  block->pend.assign(pend, pend + n);
-  block->firstPair = std::move(t.firstPair);
+  block->pend = std::move(job.pend);
+  block->firstPair = std::move(job.tiles.firstPair);
   if (m_keepSegments) {
     m_segments.reserve(m_segments.size() + count);
     for (size_t i = 0; i < count; ++i) {

@@ -7,6 +7,7 @@
 // per-segment age estimates and per-site summaries (ref: HMM.cpp:639-1041, 1087-1107, 1179-1458).
 #pragma once
 
+#include <atomic>
 #include <cstdint>
 #include <memory>
 #include <string>
@@ -131,12 +132,16 @@ private:
   };
   struct GzOut;
   struct SegmentBlock;
+  struct ChunkJob;
+  struct DecodePipeline;
 
   Data data;
   DecodingQuantities m_decodingQuant;
   DecodingParams decodingParams;
   ModelTables m_model;
   fsmc_ctx* m_ctx = nullptr;
+  fsmc_ctx* m_ctx2 = nullptr;  // second decode worker's context (narrow-kernel requests only)
+  std::unique_ptr<DecodePipeline> m_pipeline;
   int m_batchSize = 64;
   long sequenceLength = 0;
   unsigned int stateThreshold = 0, ageThreshold = 0;
@@ -163,6 +168,11 @@ private:
   std::vector<IbdSegment> m_segments;
 
   void uploadModel();
+  void uploadModelTo(fsmc_ctx*& ctx);
+  void startDecodeWorkers();
+  void drainDecodes();
+  void decodeChunk(ChunkJob& job, fsmc_ctx* ctx);
+  void completeChunk(ChunkJob& job);
   void openOutput(int jobs, int jobInd);
   void flushPending(bool all);
   void runSegmentChunk(const Pending* pairs, size_t n);
@@ -170,5 +180,5 @@ private:
   void runPosteriorSumChunk(const Pending* pairs, size_t n);
   IbdSegment toIbdSegment(const SegmentBlock& block, size_t i) const;
   void formatSegments(const SegmentBlock& block, size_t lo, size_t hi, std::string& out) const;
-  double m_segmentsPerPair = 4.0;  // densest chunk so far: sizes the next chunk's record buffer
+  std::atomic<double> m_segmentsPerPair{4.0};  // densest chunk so far: sizes the next chunk's record buffer
 };

@@ -53,6 +53,11 @@ std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vecto
   }
   const std::vector<int> order = jobOrder(params.jobs);
   std::vector<JobReport> reports(static_cast<size_t>(params.jobs));
+  // the files are read once; every job cuts its two sample windows out of the result (Data::forJob)
+  DecodingParams wholeParams = params;
+  wholeParams.jobs = 1;
+  wholeParams.jobInd = 1;
+  const Data whole(wholeParams);
   std::atomic<size_t> next{0};
   auto worker = [&](const int device) {
     for (size_t i = next++; i < order.size(); i = next++) {
@@ -67,7 +72,7 @@ std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vecto
         p.verbose = false;
         // reading, model preparation and decoding of different jobs overlap freely: the only process-wide state, the
         // std::rand sequence of the emission preparation, is seeded and consumed under its own lock (Data.cpp)
-        auto job = std::make_unique<FastSMC>(p);
+        auto job = std::make_unique<FastSMC>(p, Data::forJob(whole, p));
         job->run();
         const HMM::RunStats& st = job->hmm().getRunStats();
         rep.candidates = job->getSeedingStats().candidates;

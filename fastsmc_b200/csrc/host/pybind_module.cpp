@@ -239,6 +239,7 @@ PYBIND11_MODULE(pyASMC, m)
 
   py::class_<Data>(m, "Data")
       .def(py::init<const DecodingParams&>(), "params"_a)
+      .def_static("forJob", &Data::forJob, "whole"_a, "params"_a)
       .def_static("countHapLines", &Data::countHapLines)
       .def_static("countSamplesLines", &Data::countSamplesLines)
       .def_static(

@@ -257,3 +257,23 @@ def test_hmm_decode_returns_full_posterior_of_one_pair(asmc, oracle_mod):
     whole = np.array(hmm.decode(obs), dtype=np.float32)
     mean, _ = hmm.decodeSummarize(obs)
     np.testing.assert_allclose((whole * o.vector("expectedTimes")[:, None]).sum(axis=0), np.array(mean), rtol=1e-5)
+
+
+def test_pipelined_decode_workers_give_the_same_file(asmc, tmp_path, monkeypatch):
+    """Chunks are decoded by two workers with their own contexts when the narrow kernel runs (FastSMC_exe's default
+    conditional age estimates); they complete in submission order, so the output is byte-identical to the one-worker
+    run.  Small chunks (two reference batches each) so that the example data makes many of them."""
+    monkeypatch.setenv("FSMC_FLUSH_BATCHES", "2")
+    texts = {}
+    for workers in ("1", "2"):
+        monkeypatch.setenv("FSMC_DECODE_WORKERS", workers)
+        for hashing in (True, False):
+            kw = dict(hashing=True) if hashing else dict(hashing=False, jobInd=7, jobs=9)
+            p = _params(asmc, str(tmp_path / f"w{workers}h{int(hashing)}"), noConditionalAgeEstimates=False, **kw)
+            f = asmc.FastSMC(p)
+            f.run()
+            st = f.hmm().getRunStats()
+            assert st.decodeCalls >= 8 and st.segments == f.hmm().getNumberOfDetectedSegments() > 0
+            texts[workers, hashing] = _lines(f"{p.outFileRoot}.{p.jobInd}.{p.jobs}.FastSMC.ibd.gz")
+    for hashing in (True, False):
+        assert len(texts["1", hashing]) > 100 and texts["1", hashing] == texts["2", hashing]

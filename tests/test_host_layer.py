@@ -197,3 +197,20 @@ def test_decoding_params_defaults_and_validation(asmc):
     assert (p.jobs, p.jobInd, p.batchSize, p.time, p.gap, p.min_m, p.hashing) == (1, 1, 64, 100, 1, 1.0, False)
     q = asmc.DecodingParams(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ)
     assert q.decodingMode == asmc.DecodingMode.arrayFolded and q.foldData and q.usingCSFS and not q.FastSMC
+
+
+def test_job_data_cut_from_one_read_equals_reading_the_job(asmc):
+    """runAllJobs reads the files once and cuts every job's two sample windows out of the result (Data.forJob): the
+    same object as Data(params) reading the job from the files (ref: Data.cpp:62-80, 212-262)."""
+    whole = asmc.Data(_params(asmc))
+    for jobs in (4, 9):
+        for job_ind in range(1, jobs + 1):
+            p = _params(asmc, jobs=jobs, jobInd=job_ind)
+            a, b = asmc.Data(p), asmc.Data.forJob(whole, p)
+            assert a.IIDList == b.IIDList and a.FamIDList == b.FamIDList and len(a.IIDList) > 0
+            assert list(a.globalHapId) == list(b.globalHapId)
+            assert (a.windowSize, a.w_i, a.w_j, a.is_j_above_diag) == (b.windowSize, b.w_i, b.w_j, b.is_j_above_diag)
+            assert np.array_equal(np.array(a.hapBits), np.array(b.hapBits))
+            assert a.sites == b.sites and list(a.physicalPositions) == list(b.physicalPositions)
+            assert np.array_equal(np.array(a.geneticPositions), np.array(b.geneticPositions))
+            assert a.calculateUndistinguishedCounts(50) == b.calculateUndistinguishedCounts(50)
