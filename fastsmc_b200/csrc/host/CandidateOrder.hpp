@@ -616,34 +616,70 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   double tRehash = 0;
   int64_t numRehash = 0, rehashScanned = 0;
   size_t maxLive = 0;
+  // A rehash walks every live node in list order.  With 10^8 live nodes that is the expensive part of the replay, so
+  // each step runs on all threads: collecting the live nodes (slices of the creation ranks), sorting them, and
+  // re-keying, where every thread owns a contiguous range of the NEW buckets and handles the nodes that fall into it
+  // (a bucket's group key is set by its first node in walk order; each thread meets its nodes in walk order).
+  const unsigned nThreads = threads ? threads : std::max(1u, std::thread::hardware_concurrency());
+  auto runThreads = [&](const unsigned jobs, auto&& body) {
+    std::vector<std::thread> pool;
+    for (unsigned j = 1; j < jobs; ++j) {
+      pool.emplace_back(body, j);
+    }
+    body(0u);
+    for (auto& th : pool) {
+      th.join();
+    }
+  };
+  std::vector<uint32_t> newBucketOf;
   auto rehash = [&](const size_t newBuckets, const int w, const int64_t upTo) {
     const double r0 = trace ? clock() : 0;
     ++numRehash;
     rehashScanned += upTo;
-    scratch.clear();
     const int minEnd = w - gap - 1;
-    for (int64_t q = 0; q < upTo; ++q) {
-      if (ordered[static_cast<size_t>(q)].endWord >= minEnd) {
-        scratch.push_back(placeOf(q));
+    const unsigned T = upTo < std::min<int64_t>(int64_t{1} << 18, kBigWord) ? 1u : nThreads;
+    {
+      std::vector<std::vector<Placed>> part(T);
+      runThreads(T, [&](const unsigned t) {
+        const int64_t lo = upTo * t / T, hi = upTo * (t + 1) / T;
+        for (int64_t q = lo; q < hi; ++q) {
+          if (ordered[static_cast<size_t>(q)].endWord >= minEnd) {
+            part[t].push_back(placeOf(q));
+          }
+        }
+      });
+      scratch.clear();
+      for (const auto& v : part) {
+        scratch.insert(scratch.end(), v.begin(), v.end());
       }
     }
     parallelSort(scratch, std::less<Placed>(), threads);
     setBuckets(newBuckets);
     bucket.reset(buckets);
     const int64_t N = static_cast<int64_t>(scratch.size());
-    for (int64_t e = 0; e < N; ++e) {
-      const int64_t q = scratch[static_cast<size_t>(e)].q;
-      if (e + kAhead < N) {
-        __builtin_prefetch(&bucket[bucketOf(pairKey(scratch[static_cast<size_t>(e + kAhead)].q))], 1);
+    newBucketOf.resize(static_cast<size_t>(N));
+    runThreads(T, [&](const unsigned t) {
+      for (int64_t e = N * t / T; e < N * (t + 1) / T; ++e) {
+        newBucketOf[static_cast<size_t>(e)] = static_cast<uint32_t>(bucketOf(pairKey(scratch[static_cast<size_t>(e)].q)));
       }
-      const size_t b = bucketOf(pairKey(q));
-      if (bucket[b].live == 0) {
-        bucket[b].G = -(tick + N - e);  // groups in the order their first node is met
+    });
+    const int64_t tick0 = tick;
+    runThreads(T, [&](const unsigned t) {
+      const size_t bLo = buckets * t / T, bHi = buckets * (t + 1) / T;
+      for (int64_t e = 0; e < N; ++e) {
+        const size_t b = newBucketOf[static_cast<size_t>(e)];
+        if (b < bLo || b >= bHi) {
+          continue;
+        }
+        const int64_t q = scratch[static_cast<size_t>(e)].q;
+        if (bucket[b].live == 0) {
+          bucket[b].G = -(tick0 + N - e);  // groups in the order their first node is met
+        }
+        ++bucket[b].live;
+        nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
+        nodeW[static_cast<size_t>(q)] = -(tick0 + e);  // inside a group: reverse order of the walk
       }
-      ++bucket[b].live;
-      nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
-      nodeW[static_cast<size_t>(q)] = -(tick + e);  // inside a group: reverse order of the walk
-    }
+    });
     tick += N + 1;
     tRehash += trace ? clock() - r0 : 0;
   };

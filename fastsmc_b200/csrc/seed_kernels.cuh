@@ -213,6 +213,7 @@ __global__ void groupScatterKernel(const SeedArgs args)
 }
 
 constexpr int kPairChunk = 8;        // consecutive pair indices per thread
+constexpr int kLaneWords = 8;        // words a lane extends its own interval before the warp takes over
 constexpr int kPairBlockThreads = 256;
 constexpr unsigned long long kPairsPerChunk = static_cast<unsigned long long>(kPairChunk) * kPairBlockThreads;
 
@@ -338,42 +339,76 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
           }
         }
       }
-      // warp-level extension: serve the lanes that hold a start one after the other
-      unsigned pending = __ballot_sync(0xffffffffu, isStart);
+      // ---- extension.  Most intervals are one or two words long, so every lane first walks its own interval for up
+      // to kLaneWords words (32 independent load streams per warp instead of one interval at a time); the few that
+      // are still open after that are finished by the whole warp, 32 words per step.
+      int end = w, misses = 0, pos = w + 1;
+      bool open = isStart;
+      if (isStart) {
+        const uint64_t* A = a.haps + static_cast<size_t>(hLo) * a.wordsPerHap;
+        const uint64_t* B = a.haps + static_cast<size_t>(hHi) * a.wordsPerHap;
+        for (int k = 0; k < kLaneWords && open && pos < a.W; ++k, ++pos) {
+          if (__ldg(A + pos) == __ldg(B + pos)) {
+            end = pos;
+            misses = 0;
+          } else if (++misses > a.gap) {
+            open = false;
+          }
+        }
+        if (pos >= a.W) {
+          open = false;  // ran into the end of the chromosome
+        }
+      }
+      unsigned pending = __ballot_sync(0xffffffffu, isStart && open);
       while (pending) {
         const int src = __ffs(pending) - 1;
         pending &= pending - 1u;
         const uint32_t sLo = __shfl_sync(0xffffffffu, hLo, src), sHi = __shfl_sync(0xffffffffu, hHi, src);
+        int sEnd = __shfl_sync(0xffffffffu, end, src), sMisses = __shfl_sync(0xffffffffu, misses, src);
+        const int sPos = __shfl_sync(0xffffffffu, pos, src);
         const uint64_t* A = a.haps + static_cast<size_t>(sLo) * a.wordsPerHap;
         const uint64_t* B = a.haps + static_cast<size_t>(sHi) * a.wordsPerHap;
-        int end = w, misses = 0;
-        bool open = true;
-        for (int pos = w + 1; pos < a.W && open; pos += 32) {
-          const int x = pos + static_cast<int>(lane);
+        bool sOpen = true;
+        for (int p0 = sPos; p0 < a.W && sOpen; p0 += 32) {
+          const int x = p0 + static_cast<int>(lane);
           const bool eq = x < a.W && __ldg(A + x) == __ldg(B + x);
           const unsigned m = __ballot_sync(0xffffffffu, eq);
-          const int valid = min(32, a.W - pos);
+          const int valid = min(32, a.W - p0);
           for (int b = 0; b < valid; ++b) {  // warp-uniform walk over the 32 comparison bits
             if ((m >> b) & 1u) {
-              end = pos + b;
-              misses = 0;
-            } else if (++misses > a.gap) {
-              open = false;
+              sEnd = p0 + b;
+              sMisses = 0;
+            } else if (++sMisses > a.gap) {
+              sOpen = false;
               break;
             }
           }
         }
+        if (static_cast<int>(lane) == src) {
+          end = sEnd;
+        }
+      }
+      // ---- length filter and output, one atomic per warp (ref: HASHING/Utils.cpp:22-34, HASHING/Match.hpp:46-51)
+      bool keep = false;
+      if (isStart) {
+        const int sEnd = min(64 * end + 63, a.L - 1);
+        const float d = a.genPos[sEnd] - a.genPos[64 * w];
+        keep = (a.flags & FSMC_SEED_ALL_INTERVALS) || (100.0 * static_cast<double>(d) >= static_cast<double>(a.minLengthCm));
+      }
+      const unsigned startMask = __ballot_sync(0xffffffffu, isStart), keepMask = __ballot_sync(0xffffffffu, keep);
+      if (startMask) {
+        unsigned long long base = 0;
         if (lane == 0) {
-          atomicAdd(&a.counters[5], 1ull);
-          // ref: HASHING/Utils.cpp:22-34, HASHING/Match.hpp:46-51
-          const int sEnd = min(64 * end + 63, a.L - 1);
-          const float d = a.genPos[sEnd] - a.genPos[64 * w];
-          const bool keep = (a.flags & FSMC_SEED_ALL_INTERVALS) || (100.0 * static_cast<double>(d) >= static_cast<double>(a.minLengthCm));
-          if (keep) {
-            const unsigned long long idx = atomicAdd(&a.counters[3], 1ull);
-            if (static_cast<long long>(idx) < a.capacity) {
-              a.out[idx] = fsmc_match{sLo, sHi, w, end};
-            }
+          atomicAdd(&a.counters[5], static_cast<unsigned long long>(__popc(startMask)));
+          if (keepMask) {
+            base = atomicAdd(&a.counters[3], static_cast<unsigned long long>(__popc(keepMask)));
+          }
+        }
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (keep) {
+          const unsigned long long idx = base + __popc(keepMask & ((1u << lane) - 1u));
+          if (static_cast<long long>(idx) < a.capacity) {
+            a.out[idx] = fsmc_match{hLo, hHi, w, end};
           }
         }
       }
