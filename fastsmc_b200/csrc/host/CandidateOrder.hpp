@@ -22,6 +22,7 @@
 #include <cstdlib>
 #include <functional>
 #include <new>
+#include <stdexcept>
 #include <thread>
 #include <utility>
 #include <vector>
@@ -578,9 +579,21 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   // nodes is still in the map); W and the bucket index are kept per node.
   std::vector<int64_t> nodeW(static_cast<size_t>(n));
   std::vector<uint32_t> nodeBucket(static_cast<size_t>(n));
+  // 8 bytes per bucket (the table reaches 2 x 10^8 buckets at biobank density): the group key as a positive magnitude
+  // in the upper 40 bits, the number of the bucket's nodes in the map in the lower 24
   struct BucketState {
-    int64_t G;     // key of the bucket's group, valid while live > 0
-    int64_t live;  // nodes of the bucket in the map
+    uint64_t bits;
+    int64_t G() const { return -static_cast<int64_t>(bits >> 24); }  // valid while live() > 0
+    void setG(const int64_t g) { bits = (static_cast<uint64_t>(-g) << 24) | (bits & 0xffffffull); }
+    uint64_t live() const { return bits & 0xffffffull; }
+    void addNode()
+    {
+      if (live() == 0xffffffull) {
+        throw std::runtime_error("replayReferenceOrderFast: more than 2^24 nodes in one bucket");
+      }
+      ++bits;
+    }
+    void dropNode() { --bits; }
   };
   size_t buckets = 17, count = 0;
   HugeArray<BucketState> bucket(buckets);
@@ -609,7 +622,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     bool operator<(const Placed& o) const { return G != o.G ? G < o.G : W < o.W; }
   };
   auto placeOf = [&](const int64_t q) {
-    return Placed{bucket[nodeBucket[static_cast<size_t>(q)]].G, nodeW[static_cast<size_t>(q)], q};
+    return Placed{bucket[nodeBucket[static_cast<size_t>(q)]].G(), nodeW[static_cast<size_t>(q)], q};
   };
   std::vector<Placed> scratch;
   // nodes alive while word w's intervals are being inserted: created so far (rank < upTo), end word >= w - gap - 1
@@ -672,10 +685,10 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
           continue;
         }
         const int64_t q = scratch[static_cast<size_t>(e)].q;
-        if (bucket[b].live == 0) {
-          bucket[b].G = -(tick0 + N - e);  // groups in the order their first node is met
+        if (bucket[b].live() == 0) {
+          bucket[b].setG(-(tick0 + N - e));  // groups in the order their first node is met
         }
-        ++bucket[b].live;
+        bucket[b].addNode();
         nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
         nodeW[static_cast<size_t>(q)] = -(tick0 + e);  // inside a group: reverse order of the walk
       }
@@ -706,9 +719,10 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       }
       const size_t b = bucketOf(pairKey(q));
       BucketState& st = bucket[b];
-      if (st.live++ == 0) {
-        st.G = -tick;  // a new group goes to the front of the list
+      if (st.live() == 0) {
+        st.setG(-tick);  // a new group goes to the front of the list
       }
+      st.addNode();
       ++count;
       nodeBucket[static_cast<size_t>(q)] = static_cast<uint32_t>(b);
       nodeW[static_cast<size_t>(q)] = -tick;  // front of its group
@@ -727,9 +741,9 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
         }
         BucketState& st = bucket[nodeBucket[static_cast<size_t>(q)]];
         if (longEnough(ordered[static_cast<size_t>(q)])) {
-          leaving.push_back(Placed{st.G, nodeW[static_cast<size_t>(q)], q});  // G stays readable until the next insert
+          leaving.push_back(Placed{st.G(), nodeW[static_cast<size_t>(q)], q});  // G stays readable until the next insert
         }
-        --st.live;
+        st.dropNode();
         --count;
       }
       const double c2 = trace ? clock() : 0;
