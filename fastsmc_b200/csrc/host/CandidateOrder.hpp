@@ -510,6 +510,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       buckets = NodeOrderMap::bucketsAfter(buckets, distinct[w]);
     }
   }
+  std::vector<fsmc_match> ordered(static_cast<size_t>(n));
   lap("seed-map bucket counts");
   // A low-complexity word (a stretch of rare SNPs where most haplotypes are identical) starts millions of intervals
   // at once: such words are taken one at a time with the sort itself on all threads, the others one word per thread.
@@ -538,13 +539,14 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       int64_t rank;
       uint32_t a, b;
       int64_t index;
+      int32_t endWord;
     };
     std::vector<Creation> created;
     created.reserve(static_cast<size_t>(hi - lo));
     for (int64_t q = lo; q < hi; ++q) {
       const int64_t i = byStart[static_cast<size_t>(q)];
       const fsmc_match& m = intervals[static_cast<size_t>(i)];
-      created.push_back(Creation{rankOfNode[static_cast<size_t>(nodeOfHap[m.hapA])], m.hapA, m.hapB, i});
+      created.push_back(Creation{rankOfNode[static_cast<size_t>(nodeOfHap[m.hapA])], m.hapA, m.hapB, i, m.endWord});
     }
     auto less = [](const Creation& x, const Creation& y) {
       return x.rank != y.rank ? x.rank < y.rank : (x.a != y.a ? x.a < y.a : x.b < y.b);
@@ -554,8 +556,12 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     } else {
       std::sort(created.begin(), created.end(), less);
     }
+    // From here on an interval is named by its creation rank q (its position in byStart): everything the sequential
+    // phase touches is then laid out in the order it is visited.
     for (int64_t q = lo; q < hi; ++q) {
-      byStart[static_cast<size_t>(q)] = created[static_cast<size_t>(q - lo)].index;
+      const Creation& c = created[static_cast<size_t>(q - lo)];
+      byStart[static_cast<size_t>(q)] = c.index;
+      ordered[static_cast<size_t>(q)] = fsmc_match{c.a, c.b, w, c.endWord};
     }
   };
   parallelForWords(numWords, threads, [&](const int w) { creationOrderOfWord(w, false); });
@@ -563,14 +569,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     creationOrderOfWord(w, true);
   }
   lap("creation order per word");
-  // From here on an interval is named by its creation rank q (its position in byStart): everything the sequential
-  // phase touches is then laid out in the order it is visited.  byEnd lists the ranks by end word, ascending.
-  std::vector<fsmc_match> ordered(static_cast<size_t>(n));
-  parallelForWords(numWords, threads, [&](const int w) {
-    for (int64_t q = startBegin[w]; q < startBegin[w + 1]; ++q) {
-      ordered[static_cast<size_t>(q)] = intervals[static_cast<size_t>(byStart[static_cast<size_t>(q)])];
-    }
-  });
+  // byEnd lists the creation ranks by end word, ascending
   std::vector<int64_t> byEnd;
   groupByKey(n, numWords, threads, [&](const int64_t q) { return ordered[static_cast<size_t>(q)].endWord; }, endBegin, byEnd);
   lap("reorder, group by end word");
