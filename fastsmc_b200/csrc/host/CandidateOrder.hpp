@@ -332,22 +332,20 @@ template <class Fn> void parallelForWords(const int numWords, unsigned threads, 
   }
 }
 
-// Sort on all host threads: equal slices sorted concurrently, then rounds of pairwise in-place merges.
+// Sort on all host threads (sample sort): splitters from a sorted sample cut the key range into one part per thread;
+// every thread classifies its slice of the input, the parts are gathered by a counting scatter and sorted
+// independently.  No merge rounds, whose last ones would run on one or two threads.
 template <class T, class Less> void parallelSort(std::vector<T>& v, Less less, unsigned threads = 0)
 {
   if (threads == 0) {
     threads = std::max(1u, std::thread::hardware_concurrency());
   }
   const size_t n = v.size();
-  size_t parts = 1;
-  while (parts * 2 <= threads && n / (parts * 2) >= (size_t{1} << 16)) {
-    parts *= 2;
-  }
-  if (parts == 1) {
+  const size_t parts = std::min<size_t>({threads, n / (size_t{1} << 16), size_t{255}});  // part ids are bytes
+  if (parts < 2) {
     std::sort(v.begin(), v.end(), less);
     return;
   }
-  auto bound = [&](const size_t i) { return n * i / parts; };
   auto runAll = [&](const size_t jobs, auto&& body) {
     std::vector<std::thread> pool;
     for (size_t j = 1; j < jobs; ++j) {
@@ -358,13 +356,53 @@ template <class T, class Less> void parallelSort(std::vector<T>& v, Less less, u
       th.join();
     }
   };
-  runAll(parts, [&](const size_t j) { std::sort(v.begin() + bound(j), v.begin() + bound(j + 1), less); });
-  for (size_t width = 1; width < parts; width *= 2) {
-    runAll(parts / (2 * width), [&](const size_t j) {
-      const size_t lo = bound(2 * width * j), mid = bound(2 * width * j + width), hi = bound(2 * width * (j + 1));
-      std::inplace_merge(v.begin() + lo, v.begin() + mid, v.begin() + hi, less);
-    });
+  // splitters: every (sample / parts)-th element of a sorted, evenly spaced sample
+  const size_t sampleSize = std::min<size_t>(n, parts * 256);
+  std::vector<T> sample(sampleSize);
+  for (size_t i = 0; i < sampleSize; ++i) {
+    sample[i] = v[n / sampleSize * i];
   }
+  std::sort(sample.begin(), sample.end(), less);
+  std::vector<T> splitter(parts - 1);
+  for (size_t p = 1; p < parts; ++p) {
+    splitter[p - 1] = sample[sampleSize * p / parts];
+  }
+  auto partOf = [&](const T& x) {  // number of splitters <= x
+    return static_cast<size_t>(std::upper_bound(splitter.begin(), splitter.end(), x, less) - splitter.begin());
+  };
+  auto sliceBound = [&](const size_t t) { return n * t / parts; };
+  std::vector<std::vector<size_t>> count(parts, std::vector<size_t>(parts, 0));
+  std::vector<uint8_t> partId(n);
+  static_assert(sizeof(uint8_t) == 1, "");
+  runAll(parts, [&](const size_t t) {
+    for (size_t i = sliceBound(t); i < sliceBound(t + 1); ++i) {
+      const size_t p = partOf(v[i]);
+      partId[i] = static_cast<uint8_t>(p);
+      ++count[t][p];
+    }
+  });
+  std::vector<size_t> partBegin(parts + 1, 0);
+  {
+    size_t run = 0;
+    for (size_t p = 0; p < parts; ++p) {
+      partBegin[p] = run;
+      for (size_t t = 0; t < parts; ++t) {
+        const size_t c = count[t][p];
+        count[t][p] = run;  // where slice t writes its first element of part p
+        run += c;
+      }
+    }
+    partBegin[parts] = run;
+  }
+  std::vector<T> out(n);
+  runAll(parts, [&](const size_t t) {
+    std::vector<size_t>& cursor = count[t];
+    for (size_t i = sliceBound(t); i < sliceBound(t + 1); ++i) {
+      out[cursor[partId[i]]++] = v[i];
+    }
+  });
+  runAll(parts, [&](const size_t p) { std::sort(out.begin() + partBegin[p], out.begin() + partBegin[p + 1], less); });
+  v.swap(out);
 }
 
 // Zero-filled array for a table that is hit at random: backed by transparent huge pages where the system allows it
