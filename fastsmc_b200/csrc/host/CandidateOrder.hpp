@@ -335,7 +335,8 @@ template <class Fn> void parallelForWords(const int numWords, unsigned threads, 
 // Sort on all host threads (sample sort): splitters from a sorted sample cut the key range into one part per thread;
 // every thread classifies its slice of the input, the parts are gathered by a counting scatter and sorted
 // independently.  No merge rounds, whose last ones would run on one or two threads.
-template <class T, class Less> void parallelSort(std::vector<T>& v, Less less, unsigned threads = 0)
+template <class T, class Less>
+void parallelSort(std::vector<T>& v, Less less, unsigned threads = 0, std::vector<T>* reusable = nullptr)
 {
   if (threads == 0) {
     threads = std::max(1u, std::thread::hardware_concurrency());
@@ -394,7 +395,9 @@ template <class T, class Less> void parallelSort(std::vector<T>& v, Less less, u
     }
     partBegin[parts] = run;
   }
-  std::vector<T> out(n);
+  std::vector<T> local;
+  std::vector<T>& out = reusable ? *reusable : local;  // fresh memory is slow to fault in: callers that sort repeatedly keep it
+  out.resize(n);
   runAll(parts, [&](const size_t t) {
     std::vector<size_t>& cursor = count[t];
     for (size_t i = sliceBound(t); i < sliceBound(t + 1); ++i) {
@@ -682,6 +685,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     }
   };
   std::vector<uint32_t> newBucketOf;
+  std::vector<Placed> sortBuffer;
   auto rehash = [&](const size_t newBuckets, const int w, const int64_t upTo) {
     const double r0 = trace ? clock() : 0;
     ++numRehash;
@@ -689,21 +693,29 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     const int minEnd = w - gap - 1;
     const unsigned T = upTo < std::min<int64_t>(int64_t{1} << 18, kBigWord) ? 1u : nThreads;
     {
-      std::vector<std::vector<Placed>> part(T);
+      // two passes (count, then write in place): no per-thread vectors to grow and copy
+      std::vector<int64_t> found(T + 1, 0);
       runThreads(T, [&](const unsigned t) {
-        const int64_t lo = upTo * t / T, hi = upTo * (t + 1) / T;
-        for (int64_t q = lo; q < hi; ++q) {
+        int64_t c = 0;
+        for (int64_t q = upTo * t / T; q < upTo * (t + 1) / T; ++q) {
+          c += ordered[static_cast<size_t>(q)].endWord >= minEnd;
+        }
+        found[t + 1] = c;
+      });
+      for (unsigned t = 0; t < T; ++t) {
+        found[t + 1] += found[t];
+      }
+      scratch.resize(static_cast<size_t>(found[T]));
+      runThreads(T, [&](const unsigned t) {
+        int64_t at = found[t];
+        for (int64_t q = upTo * t / T; q < upTo * (t + 1) / T; ++q) {
           if (ordered[static_cast<size_t>(q)].endWord >= minEnd) {
-            part[t].push_back(placeOf(q));
+            scratch[static_cast<size_t>(at++)] = placeOf(q);
           }
         }
       });
-      scratch.clear();
-      for (const auto& v : part) {
-        scratch.insert(scratch.end(), v.begin(), v.end());
-      }
     }
-    parallelSort(scratch, std::less<Placed>(), threads);
+    parallelSort(scratch, std::less<Placed>(), threads, &sortBuffer);
     setBuckets(newBuckets);
     bucket.reset(buckets);
     const int64_t N = static_cast<int64_t>(scratch.size());
