@@ -21,6 +21,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <functional>
+#include <memory>
 #include <new>
 #include <stdexcept>
 #include <thread>
@@ -408,6 +409,29 @@ void parallelSort(std::vector<T>& v, Less less, unsigned threads = 0, std::vecto
   v.swap(out);
 }
 
+// Array of trivially constructible elements that is NOT zero-filled: every element is written before it is read, and
+// the first touch of a multi-GB buffer is better done by the threads that fill it than by one zeroing pass.
+template <class T> class RawArray
+{
+public:
+  RawArray() = default;
+  explicit RawArray(const size_t n) { reset(n); }
+  void reset(const size_t n)
+  {
+    mData.reset(new T[std::max<size_t>(n, 1)]);  // default-initialised: no fill for plain types
+    mSize = n;
+  }
+  size_t size() const { return mSize; }
+  T* data() { return mData.get(); }
+  const T* data() const { return mData.get(); }
+  T& operator[](const size_t i) { return mData[i]; }
+  const T& operator[](const size_t i) const { return mData[i]; }
+
+private:
+  std::unique_ptr<T[]> mData;
+  size_t mSize = 0;
+};
+
 // Zero-filled array for a table that is hit at random: backed by transparent huge pages where the system allows it
 // (a 25 MB table on 4 KB pages misses the TLB on nearly every access, and page walks are slow under virtualisation).
 template <class T> class HugeArray
@@ -449,7 +473,7 @@ private:
 // counts and scatters on its own.
 template <class KeyFn>
 void groupByKey(const int64_t n, const int numKeys, unsigned threads, KeyFn&& key, std::vector<int64_t>& begin,
-                std::vector<int64_t>& out)
+                RawArray<int64_t>& out)
 {
   if (threads == 0) {
     threads = std::max(1u, std::thread::hardware_concurrency());
@@ -484,7 +508,7 @@ void groupByKey(const int64_t n, const int numKeys, unsigned threads, KeyFn&& ke
     }
   }
   begin[static_cast<size_t>(numKeys)] = runTotal;
-  out.resize(static_cast<size_t>(n));
+  out.reset(static_cast<size_t>(n));
   run([&](const int t) {
     const auto [lo, hi] = slice(t);
     std::vector<int64_t>& cursor = hist[static_cast<size_t>(t)];
@@ -494,8 +518,8 @@ void groupByKey(const int64_t n, const int numKeys, unsigned threads, KeyFn&& ke
   });
 }
 
-template <class WordFn, class LengthFn, class EmitFn>
-void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const uint32_t numHaps, const int numWords,
+template <class Intervals, class WordFn, class LengthFn, class EmitFn>
+void replayReferenceOrderFast(const Intervals& intervals, const uint32_t numHaps, const int numWords,
                               const int gap, WordFn&& rawWord, LengthFn&& longEnough, EmitFn&& emit,
                               const unsigned threads = 0)
 {
@@ -514,7 +538,8 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
     }
   };
   // ---- intervals grouped by start word ---------------------------------------------------------------------------
-  std::vector<int64_t> startBegin, endBegin, byStart;
+  std::vector<int64_t> startBegin, endBegin;
+  RawArray<int64_t> byStart;
   groupByKey(n, numWords, threads, [&](const int64_t i) { return intervals[static_cast<size_t>(i)].startWord; }, startBegin,
              byStart);
   if (trace) {
@@ -551,7 +576,7 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
       buckets = NodeOrderMap::bucketsAfter(buckets, distinct[w]);
     }
   }
-  std::vector<fsmc_match> ordered(static_cast<size_t>(n));
+  RawArray<fsmc_match> ordered(static_cast<size_t>(n));
   lap("seed-map bucket counts");
   // A low-complexity word (a stretch of rare SNPs where most haplotypes are identical) starts millions of intervals
   // at once: such words are taken one at a time with the sort itself on all threads, the others one word per thread.
@@ -611,14 +636,14 @@ void replayReferenceOrderFast(const std::vector<fsmc_match>& intervals, const ui
   }
   lap("creation order per word");
   // byEnd lists the creation ranks by end word, ascending
-  std::vector<int64_t> byEnd;
+  RawArray<int64_t> byEnd;
   groupByKey(n, numWords, threads, [&](const int64_t q) { return ordered[static_cast<size_t>(q)].endWord; }, endBegin, byEnd);
   lap("reorder, group by end word");
   // ---- phase 2: the extend map's node order as (G, W) keys ------------------------------------------------------
   // G lives in the bucket table (valid while the bucket is non-empty, so it can be read whenever one of the bucket's
   // nodes is still in the map); W and the bucket index are kept per node.
-  std::vector<int64_t> nodeW(static_cast<size_t>(n));
-  std::vector<uint32_t> nodeBucket(static_cast<size_t>(n));
+  RawArray<int64_t> nodeW(static_cast<size_t>(n));
+  RawArray<uint32_t> nodeBucket(static_cast<size_t>(n));
   // 8 bytes per bucket (the table reaches 2 x 10^8 buckets at biobank density): the group key as a positive magnitude
   // in the upper 40 bits, the number of the bucket's nodes in the map in the lower 24
   struct BucketState {

@@ -73,13 +73,14 @@ void ASMC::FastSMC::seedAndDecode()
   // the order replay groups the intervals itself: no need for the canonical sort
   sp.flags = mParams.referenceCandidateOrder ? (FSMC_SEED_ALL_INTERVALS | FSMC_SEED_UNSORTED) : 0u;
 
-  std::vector<fsmc_match> found(std::max<size_t>(1u << 16, static_cast<size_t>(H) * 8));
+  // not zero-filled: at biobank density the intervals are gigabytes, written once by the copy from the device
+  candidate_order::RawArray<fsmc_match> buffer(std::max<size_t>(1u << 16, static_cast<size_t>(H) * 8));
   const double t0 = now();
   for (;;) {
     const int rc =
-        fsmc_seed(mHmm.context(), &sp, found.data(), static_cast<int64_t>(found.size()), &mSeedStats.device);
+        fsmc_seed(mHmm.context(), &sp, buffer.data(), static_cast<int64_t>(buffer.size()), &mSeedStats.device);
     if (rc == FSMC_E_OVERFLOW) {
-      found.resize(static_cast<size_t>(mSeedStats.device.numMatches) + 1024);
+      buffer.reset(static_cast<size_t>(mSeedStats.device.numMatches) + 1024);
       continue;
     }
     if (rc != FSMC_OK) {
@@ -87,7 +88,12 @@ void ASMC::FastSMC::seedAndDecode()
     }
     break;
   }
-  found.resize(static_cast<size_t>(mSeedStats.device.numMatches));
+  struct Found {  // the filled part of the buffer
+    const fsmc_match* p;
+    size_t n;
+    size_t size() const { return n; }
+    const fsmc_match& operator[](const size_t i) const { return p[i]; }
+  } const found{buffer.data(), static_cast<size_t>(mSeedStats.device.numMatches)};
   mSeedStats.seedWallS = now() - t0;
 
   mCandidates.clear();
@@ -102,8 +108,8 @@ void ASMC::FastSMC::seedAndDecode()
     }
   };
   if (!mParams.referenceCandidateOrder) {
-    for (const fsmc_match& m : found) {
-      submit(m);
+    for (size_t i = 0; i < found.size(); ++i) {
+      submit(found[i]);
     }
   } else {
     const double t1 = now();
