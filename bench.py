@@ -31,6 +31,7 @@ sys.path.insert(0, ROOT)
 N_HAPS, N_SITES, SPAN_BP, CHROM, SEED = 1000, 10_000, 30_000_000, 1, 20201117 + 2
 DQ = os.path.join(ROOT, "data", "30-100-2000.decodingQuantities.gz")
 FLOPS_PER_PAIR_SITE_STATE = 35  # 15 forward + 15 backward + 3 combine + 2 consume
+NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE = (6.072805e9 + 6.078759e9) / (37888 * 10000)  # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt
 NCU_DRAM_BYTES_PER_PAIR_SITE = (109.922461e9 + 109.458343e9) / (37888 * 10000)  # profiles/r1_v4_decodeFast_s69_ncu_full.txt
 WORKLOAD = "cfg2: all-pairs, hashing off, 1000 haplotypes x 10000 SNPs, S=69 (30-100-2000), time=50, batchSize=32"
 
@@ -354,7 +355,10 @@ def main():
             "default_flags": dict(narrow, roofline={"bound": "fp32", "achieved": narrow["value"] / world * FLOPS_PER_PAIR_SITE_STATE * S / 1e12,
                                                      "peak": fp32_peak, "unit": "TFLOP/s",
                                                      "frac": narrow["value"] / world * FLOPS_PER_PAIR_SITE_STATE * S / 1e12 / fp32_peak,
-                                                     "traffic": None}),
+                                                     # DRAM bytes of one launch, from the ncu --set full capture
+                                                     # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt (12.15 GB for
+                                                     # 37 888 pairs x 10 000 sites), scaled by pair-sites
+                                                     "traffic": NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE * pair_sites}),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
             "ibd_wall": ibd_wall,
         }
