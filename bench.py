@@ -113,56 +113,82 @@ class ClockSampler:
                 "power_w_max": max(float(r[2]) for r in ok), "samples": len(ok), "reasons": reasons}
 
 
-def run_reference(args, rank, world):
-    """CPU arm: the oracle (kind "port") on all host threads, each step a bounded sample of cfg2's batches."""
-    if rank != 0:
-        return
+REF_JOBS = 64  # the CPU arm cuts cfg2 into 64 jobs (reference jobs/jobInd) and runs one job per host core at a time
+
+
+def reference_sample(cores):
+    """One bounded sample of cfg2 on the reference's own CPU implementation: `cores` concurrent processes (the reference is
+    single-threaded; its way to use many cores is one process per job, cpp_example/FastSMC_example_multiple_jobs.sh), each
+    ASMC::FastSMC(params).run() of one of the REF_JOBS jobs of the data set, all 10,000 sites, same flags as the GPU arm.
+    Returns (pair_sites, seconds of the slowest process's run(), kind, sample description).  Time excludes reading the
+    data and preparing the model, as the GPU arm's does."""
+    import re
     from oracle import pyoracle
     root = make_dataset(0)
-    cores = os.cpu_count() or 1
+    if pyoracle.reference_binary("avx") is None:
+        return None
+    procs = []
+    # off-diagonal jobs only (job ids that are perfect squares are the diagonal jobs, a quarter of the pairs), so that the
+    # concurrent processes carry equal work and the slowest one does not understate the CPU rate
+    off_diagonal = [j for j in range(1, REF_JOBS + 1) if int(j ** 0.5) ** 2 != j]
+    for k in range(cores):
+        argv = pyoracle.reference_command("avx", root, DQ, f"/tmp/fsmc_bench/ref_out_{k}", hashing=0, jobs=REF_JOBS,
+                                          jobInd=off_diagonal[k % len(off_diagonal)], time=50, noConditionalAgeEstimates=1,
+                                          batchSize=32)
+        procs.append(subprocess.Popen(argv, stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True))
+    pairs, slowest = 0, 0.0
+    for pr in procs:
+        out, err = pr.communicate()
+        if pr.returncode != 0:
+            raise RuntimeError("reference build failed: " + err[-300:])
+        slowest = max(slowest, json.loads(out.strip().splitlines()[-1])["run_s"])
+        pairs += int(re.search(r"Decoded (\d+) pairs", out + err).group(1))
+    sample = (f"{cores} concurrent processes of the reference (unmodified sources, -O3 -DAVX -mavx), each one job of cfg2 cut "
+              f"into {REF_JOBS} jobs (jobs/jobInd): {pairs} pairs x {N_SITES} sites per step")
+    return float(pairs) * N_SITES, slowest, "reference", sample
+
+
+def port_sample(cores, n_pairs):
+    from oracle import pyoracle
+    pyoracle.build()
+    _declare_sample(pyoracle)
+    root = make_dataset(0)
     o = pyoracle.Oracle(root, DQ, "/tmp/fsmc_bench/ref_out", hashing=False, time=50, noConditionalAgeEstimates=True,
                         doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
-    batches_per_step = max(cores * 2, 16)  # ~10 s of CPU work per step on a 16-core host
-    n_pairs = batches_per_step * 32
-    sample = f"first {n_pairs} pairs ({batches_per_step} reference batches) of the job x {N_SITES} sites per step"
-    times, pair_sites = [], 0.0
+    t0 = time.time()
+    ps = pyoracle.lib().fo_decode_sample(o._h, n_pairs, cores)
+    return ps, time.time() - t0, "port", f"first {n_pairs} pairs of the job x {N_SITES} sites, {cores} threads (oracle port)"
+
+
+def run_reference(args, rank, world):
+    """CPU arm: the reference's own implementation (oracle/_ref/ref_fastsmc_avx, kind "reference"; the oracle port if that
+    binary is absent) on all host cores, each step a bounded sample of cfg2."""
+    if rank != 0:
+        return
+    cores = os.cpu_count() or 1
+    times, pair_sites, kind, sample = [], 0.0, "port", ""
     for it in range(args.warmup + args.steps):
-        t0 = time.time()
-        ps = pyoracle.lib().fo_decode_sample(o._h, n_pairs, cores) if hasattr(pyoracle.lib(), "fo_decode_sample") else -1.0
-        dt = time.time() - t0
+        r = reference_sample(cores) or port_sample(cores, 32 * max(cores * 2, 16))
         if it >= args.warmup:
-            times.append(dt)
-            pair_sites = ps
+            times.append(r[1])
+            pair_sites, kind, sample = r[0], r[2], r[3]
     ms = 1e3 * float(np.mean(times))
     value = pair_sites / (ms / 1e3)
     line = {"impl": "reference", "metric": "hmm_pair_sites_per_s", "value": value, "unit": "pair-sites/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": WORKLOAD},
-            "cpu_baseline": {"value": value, "unit": "pair-sites/s", "cores": cores, "kind": "port", "sample": sample},
+            "cpu_baseline": {"value": value, "unit": "pair-sites/s", "cores": cores, "kind": kind, "sample": sample,
+                             "per_thread": value / cores},
             "e2e": {"value": value, "unit": "pair-sites/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(seconds_budget=15.0):
-    from oracle import pyoracle
-    root = make_dataset(0)
+def cpu_baseline():
     cores = os.cpu_count() or 1
-    o = pyoracle.Oracle(root, DQ, "/tmp/fsmc_bench/ref_out", hashing=False, time=50, noConditionalAgeEstimates=True,
-                        doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
-    n_pairs = 32 * cores
-    t0 = time.time()
-    ps = pyoracle.lib().fo_decode_sample(o._h, n_pairs, cores)
-    dt = time.time() - t0
-    # scale the sample so that it takes roughly the budget
-    scale = int(max(1, min(8, seconds_budget / max(dt, 1e-3))))
-    if scale > 1:
-        n_pairs *= scale
-        t0 = time.time()
-        ps = pyoracle.lib().fo_decode_sample(o._h, n_pairs, cores)
-        dt = time.time() - t0
-    return {"value": ps / dt, "unit": "pair-sites/s", "cores": cores, "kind": "port",
-            "sample": f"first {n_pairs} pairs of the job x {N_SITES} sites, {cores} threads, {dt:.1f} s"}
+    ps, dt, kind, sample = reference_sample(cores) or port_sample(cores, 64 * cores)
+    return {"value": ps / dt, "unit": "pair-sites/s", "cores": cores, "kind": kind, "sample": sample + f", {dt:.1f} s",
+            "per_thread": ps / dt / cores}
 
 
 def max_over_ranks(value, world, device="cuda"):
@@ -190,9 +216,6 @@ def main():
     local = int(os.environ.get("LOCAL_RANK", 0))
 
     if args.impl == "reference":
-        from oracle import pyoracle
-        pyoracle.build()
-        _declare_sample(pyoracle)
         run_reference(args, rank, world)
         return
 
@@ -363,9 +386,6 @@ def main():
             "ibd_wall": ibd_wall,
         }
         if world == 1 and not args.no_cpu_baseline:
-            from oracle import pyoracle
-            pyoracle.build()
-            _declare_sample(pyoracle)
             line["cpu_baseline"] = cpu_baseline()
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -252,3 +252,35 @@ def get_to_position(gen, to, cm=0.5):
 def cm_between(w1, w2, gen, word_size=64):
     g = np.ascontiguousarray(gen, np.float32)
     return float(lib().fo_cm_between(w1, w2, _ptr(g), len(g), word_size))
+
+
+# ---- the reference's own sources, compiled unmodified against oracle/shim (oracle/Makefile: ref_fastsmc_avx / _nosse) ----
+
+def reference_binary(flavour="avx"):
+    """Path of the reference build of that SIMD flavour, or None when it has not been built (it is built by `make` in this
+    directory wherever /root/reference exists; the GPU box receives the prebuilt file with the snapshot)."""
+    path = os.path.join(_HERE, "_ref", f"ref_fastsmc_{flavour}")
+    return path if os.access(path, os.X_OK) else None
+
+
+def reference_command(flavour, in_file_root, decoding_quant_file, out_file_root, **options):
+    """argv of one reference run: ASMC::FastSMC(params).run() with the reference's DecodingParams fields set from
+    `options` (hashing, jobs, jobInd, time, min_m, skip, gap, max_seeds, batchSize, noConditionalAgeEstimates, bin, ...)."""
+    exe = reference_binary(flavour)
+    if exe is None:
+        raise FileNotFoundError(f"oracle/_ref/ref_fastsmc_{flavour} is not built")
+    argv = [exe, f"in={in_file_root}", f"dq={decoding_quant_file}", f"out={out_file_root}"]
+    for k, v in options.items():
+        argv.append(f"{k}={int(v) if isinstance(v, bool) else v}")
+    return argv
+
+
+def reference_run(flavour, in_file_root, decoding_quant_file, out_file_root, **options):
+    """Run the reference build once; returns (timings dict, stderr text).  The output file is
+    <out_file_root>.<jobInd>.<jobs>.FastSMC.ibd.gz, named by the reference itself."""
+    import json
+    r = subprocess.run(reference_command(flavour, in_file_root, decoding_quant_file, out_file_root, **options),
+                       capture_output=True, text=True)
+    if r.returncode != 0:
+        raise RuntimeError(f"reference build failed ({r.returncode}): {r.stderr[-400:]}")
+    return json.loads(r.stdout.strip().splitlines()[-1]), r.stderr
