@@ -9,8 +9,11 @@ One "step" = one pass of the hot path over the whole job (499,500 haplotype pair
   value : pair-sites/s with the pair list resident in HBM (fsmc_plan_launch only inside the timed region)
   e2e   : the same through the C-ABI call fsmc_decode with HOST buffers: pair lists copied H2D and the segment records
           copied D2H inside the timed region
-Under torchrun each rank owns one GPU and decodes one job of that size (jobs are independent: no collective on the data
-path); value = all ranks' pair-sites / max-over-ranks device time  ("scaling": "weak").
+Under torchrun (N > 1) the SAME job is split over the N GPUs ("scaling": "strong"): the job's reference batches of 32 pairs
+are independent once formed, so rank r decodes the r-th contiguous share of them (no collective on the data path; the
+barrier and the max-over-ranks time are the only cross-rank operations); value = the job's pair-sites / the slowest rank's
+device time.  `jobs_run` is the north star's jobs/jobInd partition on a hashing workload (cfg4 family): the J = 64 jobs of one
+data set dealt to the N ranks from a shared counter, files to .ibd.gz, host and kernel seconds per rank.
 
 --impl reference times the CPU restatement of the reference algorithm (oracle/, multi-threaded over batches, AVX2 lane
 vectorisation like the reference's SIMD build) on a bounded sample of the same workload on the host cores.
@@ -62,7 +65,12 @@ def all_pairs_in_reference_order(n_ind):
     return np.concatenate(a).astype(np.uint32), np.concatenate(b).astype(np.uint32)
 
 
-def tiles_for(a, b, sites):
+def rank_share(n_batches, world, rank):
+    """Batches [lo, hi) of the job that `rank` decodes: contiguous, sizes differ by at most one."""
+    return n_batches * rank // world, n_batches * (rank + 1) // world
+
+
+def tiles_for(a, b, sites, world=1, rank=0):
     n = len(a)
     T = (n + 31) // 32
     A = np.zeros(T * 32, np.uint32)
@@ -70,9 +78,12 @@ def tiles_for(a, b, sites):
     A[:n], B[:n] = a, b
     tp = np.full(T, 32, np.int32)
     tp[-1] = n - 32 * (T - 1)
+    lo, hi = rank_share(T, world, rank)
+    A, B, tp = A.reshape(T, 32)[lo:hi], B.reshape(T, 32)[lo:hi], tp[lo:hi]
+    T = hi - lo
     z, e = np.zeros(T, np.int32), np.full(T, sites, np.int32)
-    return dict(hapA=A.reshape(T, 32), hapB=B.reshape(T, 32), tilePairs=tp, tileFrom=z, tileTo=e, tileScanFrom=z,
-                tileScanTo=e, rows=np.arange(n))
+    return dict(hapA=np.ascontiguousarray(A), hapB=np.ascontiguousarray(B), tilePairs=np.ascontiguousarray(tp), tileFrom=z,
+                tileTo=e, tileScanFrom=z, tileScanTo=e, rows=np.arange(int(tp.sum())))
 
 
 class ClockSampler:
@@ -202,6 +213,100 @@ def max_over_ranks(value, world, device="cuda"):
     return float(t.item())
 
 
+def sum_over_ranks(value, world, device="cuda"):
+    if world == 1:
+        return value
+    import torch
+    import torch.distributed as dist
+    t = torch.tensor([float(value)], dtype=torch.float64, device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.SUM)
+    return float(t.item())
+
+
+JOBS_SAMPLES = int(os.environ.get("FSMC_BENCH_JOBS_SAMPLES", 12000))  # diploid samples of the cfg4-family data set
+JOBS_SITES, JOBS_SPAN_BP, JOBS_CHROM, JOBS_J = 18022, 64_000_000, 20, 64   # chr20 array SNPs
+
+
+def jobs_run(asmc, rank, world, local, dist):
+    """North-star partition (BASELINE.json configs[3] family): ONE data set, hashing + decoding with FastSMC_exe's default
+    flags, cut into J = 64 jobs by the reference's jobs/jobInd geometry; the ranks take job indices from a shared counter
+    (longest first) and each job is one ASMC::FastSMC(params, Data::forJob(whole, params)).run(), writing its own
+    <out>.<jobInd>.<jobs>.FastSMC.ibd.gz.  No collective on the data path.  Returns (rank 0) the job-set wall time = slowest
+    rank, and the host/kernel seconds per rank that explain it."""
+    import torch
+    from fastsmc_b200 import synth
+    root = f"/tmp/fsmc_bench/cfg4s_{JOBS_SAMPLES}x{JOBS_SITES}"
+    if rank == 0 and not os.path.exists(root + ".hap.gz"):
+        synth.dataset(root, 2 * JOBS_SAMPLES, JOBS_SITES, JOBS_SPAN_BP, JOBS_CHROM, SEED + 2)
+    if dist:
+        dist.barrier()
+    p = asmc.DecodingParams()
+    p.verbose = False
+    p.inFileRoot, p.decodingQuantFile, p.outFileRoot = root, DQ, f"/tmp/fsmc_bench/jobs_out/r{rank}"
+    os.makedirs("/tmp/fsmc_bench/jobs_out", exist_ok=True)
+    p.decodingModeString, p.foldData, p.usingCSFS = "array", True, True
+    p.FastSMC, p.hashing, p.batchSize, p.time, p.min_m = True, True, 32, 50, 1.5
+    p.doPerPairMAP = p.doPerPairPosteriorMean = p.outputIbdSegmentLength = True
+    p.useKnownSeed = True
+    p.device = local
+    p.jobs, p.jobInd = 1, 1
+    p.validateParamsFastSMC()
+    t0 = time.perf_counter()
+    whole = asmc.Data(p)
+    read_s = time.perf_counter() - t0
+    p.jobs = JOBS_J
+    order = asmc.pyASMC.jobOrder(JOBS_J)
+    if dist:
+        store = dist.distributed_c10d._get_default_store()
+        key = "fsmc_jobs_next"
+        def next_job():
+            i = store.add(key, 1) - 1
+            return order[i] if i < len(order) else 0
+        dist.barrier()
+    else:
+        it = iter(order)
+        def next_job():
+            return next(it, 0)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    # two host threads on the rank's GPU: one job's host stages overlap the other's kernels
+    reports = asmc.pyASMC.runJobs(p, whole, next_job, [local, local])
+    wall = time.perf_counter() - t0
+    errors = [r.error for r in reports if r.error]
+    if errors:
+        raise RuntimeError("jobs_run: " + errors[0])
+    mine = {"rank": rank, "jobs": len(reports), "wall_s": wall, "read_s": read_s,
+            "pair_sites": sum(r.pairSites for r in reports), "candidates": sum(r.candidates for r in reports),
+            "segments": sum(r.segments for r in reports),
+            "decode_kernel_s": sum(r.kernelMs for r in reports) / 1e3, "seed_kernel_s": sum(r.seedMs for r in reports) / 1e3,
+            "host_prepare_s": sum(r.prepareSeconds for r in reports), "host_seed_call_s": sum(r.seedSeconds for r in reports),
+            "host_order_s": sum(r.orderSeconds for r in reports), "host_decode_calls_s": sum(r.decodeSeconds for r in reports),
+            "host_output_s": sum(r.outputSeconds for r in reports)}
+    if dist:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, mine)
+    else:
+        gathered = [mine]
+    if rank != 0:
+        return None
+    slowest = max(gathered, key=lambda g: g["wall_s"])
+    total_ps = sum(g["pair_sites"] for g in gathered)
+    stages = {k: slowest[k] for k in ("decode_kernel_s", "seed_kernel_s", "host_prepare_s", "host_seed_call_s", "host_order_s",
+                                      "host_decode_calls_s", "host_output_s")}
+    host_stages = {k: v for k, v in stages.items() if k.startswith("host_")}
+    return {"workload": f"cfg4 family: {JOBS_SAMPLES} synthetic diploid samples x {JOBS_SITES} chr20 array SNPs, hashing + decoding "
+                        f"(min_m 1.5, time 50, FastSMC_exe default flags), J = {JOBS_J} jobs (jobs/jobInd) dealt to {world} GPU(s) "
+                        "from a shared counter, 2 host threads per GPU, files -> per-job .ibd.gz",
+            "scaling": "strong", "n_gpus": world, "wall_s": slowest["wall_s"], "pair_sites": total_ps,
+            "pair_sites_per_s": total_ps / slowest["wall_s"], "candidates": sum(g["candidates"] for g in gathered),
+            "segments": sum(g["segments"] for g in gathered), "read_s_per_rank": max(g["read_s"] for g in gathered),
+            "host_cores": os.cpu_count(),
+            "slowest_rank": slowest,
+            "limiting_stage": max(host_stages, key=host_stages.get) if sum(host_stages.values()) > 2 * (stages["decode_kernel_s"] + stages["seed_kernel_s"]) else "kernels",
+            "note": "stage seconds are summed over the rank's jobs (two jobs run concurrently, so they can exceed wall_s)",
+            "per_rank": gathered}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -210,6 +315,7 @@ def main():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-run", action="store_true", help="skip the one-off FastSMC.run() wall-clock measurement")
+    ap.add_argument("--no-jobs-run", action="store_true", help="skip the jobs/jobInd-partitioned hashing run (jobs_run)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -227,7 +333,11 @@ def main():
     from fastsmc_b200 import _native as N, asmc
 
     # ---- host layer: data set -> Data -> model tables (the product's own code; the oracle is not involved) ----------
-    root = make_dataset(rank)
+    if rank == 0:
+        make_dataset(0)
+    if world > 1:
+        dist.barrier()
+    root = dataset_root(0)
     p = asmc.DecodingParams()
     p.verbose = False
     p.inFileRoot, p.decodingQuantFile, p.outFileRoot = root, DQ, f"/tmp/fsmc_bench/r{rank}/out"
@@ -249,9 +359,10 @@ def main():
     ctx.set_model(**tables)
     ctx.set_haplotypes(data.hapBits, L)
     a, b = all_pairs_in_reference_order(len(data.IIDList))
-    tiles = tiles_for(a, b, L)
+    tiles = tiles_for(a, b, L, world, rank)  # this rank's share of the job's batches
     flags = N.CALL_SEGMENTS | N.SEG_AGE
-    pair_sites = float(len(a)) * L
+    pair_sites = float(len(a)) * L                       # the whole job
+    my_pair_sites = float(tiles["tilePairs"].sum()) * L  # this rank's share
 
     def barrier():
         if world > 1:
@@ -281,7 +392,8 @@ def main():
     plan.close()
     total_ms = max_over_ranks(total_ms, world)
     ms_per_step = total_ms / args.steps
-    value = world * pair_sites / (ms_per_step / 1e3)
+    value = pair_sites / (ms_per_step / 1e3)
+    n_segments = int(sum_over_ranks(n_segments, world))
 
     # ---- the same job with FastSMC's command-line default age estimates (conditional on TMRCA < time, i.e.
     # noConditionalAgeEstimates off: only the states below the threshold are consumed -> decodeNarrowKernel) ------------
@@ -299,11 +411,12 @@ def main():
         plan2.launch()
     e1.record(stream)
     barrier()
-    narrow_ms = max_over_ranks(e0.elapsed_time(e1), world) / args.steps
+    narrow_rank0_ms = e0.elapsed_time(e1) / args.steps
+    narrow_ms = max_over_ranks(narrow_rank0_ms * args.steps, world) / args.steps
     r2 = plan2.collect()
-    narrow = {"value": world * pair_sites / (narrow_ms / 1e3), "unit": "pair-sites/s", "ms_per_step": narrow_ms,
+    narrow = {"value": pair_sites / (narrow_ms / 1e3), "unit": "pair-sites/s", "ms_per_step": narrow_ms,
               "kernel": "decodeNarrowKernel<69>" if r2.stats.narrowKernel else "decodeFastKernel<69>",
-              "segments_per_step": int(r2.stats.numSegments), "scratch_bytes": int(r2.stats.scratchBytes),
+              "segments_per_step": int(sum_over_ranks(int(r2.stats.numSegments), world)), "scratch_bytes": int(r2.stats.scratchBytes),
               "flags": "as the headline run but age estimates conditional on TMRCA < time (FastSMC_exe default)"}
     plan2.close()
     ctx2.close()
@@ -320,13 +433,13 @@ def main():
     e2e_s = max_over_ranks(e2e_s, world)
     h2d = sum(tiles[k].nbytes for k in ("hapA", "hapB", "tilePairs", "tileFrom", "tileTo", "tileScanFrom", "tileScanTo"))
     d2h = int(res.stats.numSegments) * N.SEGMENT_DTYPE.itemsize + 16
-    e2e = {"value": world * pair_sites / e2e_s, "unit": "pair-sites/s", "h2d_bytes_per_step": int(h2d),
+    e2e = {"value": pair_sites / e2e_s, "unit": "pair-sites/s", "h2d_bytes_per_step": int(h2d),
            "d2h_bytes_per_step": int(d2h), "ms_per_step": 1e3 * e2e_s,
            "call": "fsmc_decode (host pair lists in, host segment records out)"}
 
     # ---- one whole FastSMC.run(): read files, model preparation, decode, write .ibd.gz ------------------------------------
     ibd_wall = None
-    if not args.no_e2e_run and rank == 0:
+    if not args.no_e2e_run and rank == 0 and world == 1:
         t0 = time.perf_counter()
         f = asmc.FastSMC(p)
         f.run()
@@ -334,6 +447,10 @@ def main():
                     "decode_wall_s": f.hmm().getRunStats().decodeWallS, "output_wall_s": f.hmm().getRunStats().outputWallS,
                     "what": "FastSMC(params).run(): .hap.gz/.map/.samples + decoding quantities -> .ibd.gz"}
         del f
+
+    jobs = None
+    if not args.no_jobs_run:
+        jobs = jobs_run(asmc, rank, world, local, dist if world > 1 else None)
 
     if rank == 0:
         peaks = {}
@@ -347,43 +464,45 @@ def main():
         # algorithmic HBM bytes per pair-site of this kernel design: the backward sweep writes beta[S] floats and the
         # forward sweep reads them back (8*S), plus 2 bits of genotype input per pair-site (0.25 B)
         bytes_per_pair_site = 8.0 * S + 0.25
-        achieved = pair_sites * bytes_per_pair_site / (kernel_ms / 1e3) / 1e9
+        achieved = my_pair_sites * bytes_per_pair_site / (kernel_ms / 1e3) / 1e9  # rank 0's launches
         prop = torch.cuda.get_device_properties(local)
         fp32_peak = prop.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
-        fp32_achieved = pair_sites * FLOPS_PER_PAIR_SITE_STATE * S / (kernel_ms / 1e3) / 1e12
+        fp32_achieved = my_pair_sites * FLOPS_PER_PAIR_SITE_STATE * S / (kernel_ms / 1e3) / 1e12
         line = {
             "metric": "hmm_pair_sites_per_s", "value": value, "unit": "pair-sites/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+            "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "pairs_per_gpu": int(len(a)), "sites": int(L), "states": int(S),
-                       "pair_sites_per_step_per_gpu": pair_sites, "segments_per_step": n_segments,
+            "config": {"workload": WORKLOAD, "pairs": int(len(a)), "sites": int(L), "states": int(S),
+                       "pair_sites_per_step": pair_sites, "pair_sites_per_step_rank0": my_pair_sites,
+                       "segments_per_step": n_segments,
                        "flags": "segment length + per-segment posterior mean + MAP over ALL states (noConditionalAgeEstimates), "
                                 "the reference's regression-test / FastSMC-constructor defaults",
                        "l2": f"no flush needed: each step streams {scratch_bytes / 2**30:.0f} GiB of backward-sweep scratch "
-                             "through HBM (>> 126 MB L2)", "parallelism": f"{world} independent jobs, one per GPU"},
+                             "through HBM (>> 126 MB L2)", "parallelism": f"the job's {(len(a) + 31) // 32} reference batches dealt to {world} GPU(s) in contiguous shares; "
+                                      "no collective on the data path"},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
                          "frac": achieved / hbm_peak,
                          # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full
                          # capture (profiles/r1_v4_decodeFast_s69_ncu_full.txt: 219.38 GB for 37 888 pairs x 10 000
                          # sites = 579.0 B per pair-site, the padding of 69 states to 72 included), scaled to this
                          # launch's pair-sites
-                         "traffic": NCU_DRAM_BYTES_PER_PAIR_SITE * pair_sites,
+                         "traffic": NCU_DRAM_BYTES_PER_PAIR_SITE * my_pair_sites,
                          "traffic_source": "ncu --set full capture of a 37888-pair launch, scaled by pair-sites",
-                         "algorithmic_bytes": bytes_per_pair_site * pair_sites, "peak_source": peak_src,
+                         "algorithmic_bytes": bytes_per_pair_site * my_pair_sites, "peak_source": peak_src,
                          "kernel": "decodeFastKernel<69>", "kernel_ms": kernel_ms,
                          "algorithmic_bytes_per_pair_site": bytes_per_pair_site},
             "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
                               "flops_per_pair_site": FLOPS_PER_PAIR_SITE_STATE * S,
                               "peak_source": "SMs x 128 lanes x 2 x 1.965 GHz (nominal)"},
-            "default_flags": dict(narrow, roofline={"bound": "fp32", "achieved": narrow["value"] / world * FLOPS_PER_PAIR_SITE_STATE * S / 1e12,
+            "default_flags": dict(narrow, roofline={"bound": "fp32", "achieved": my_pair_sites / (narrow_rank0_ms / 1e3) * FLOPS_PER_PAIR_SITE_STATE * S / 1e12,
                                                      "peak": fp32_peak, "unit": "TFLOP/s",
-                                                     "frac": narrow["value"] / world * FLOPS_PER_PAIR_SITE_STATE * S / 1e12 / fp32_peak,
+                                                     "frac": my_pair_sites / (narrow_rank0_ms / 1e3) * FLOPS_PER_PAIR_SITE_STATE * S / 1e12 / fp32_peak,
                                                      # DRAM bytes of one launch, from the ncu --set full capture
                                                      # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt (12.15 GB for
                                                      # 37 888 pairs x 10 000 sites), scaled by pair-sites
-                                                     "traffic": NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE * pair_sites}),
+                                                     "traffic": NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE * my_pair_sites}),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
-            "ibd_wall": ibd_wall,
+            "ibd_wall": ibd_wall, "jobs_run": jobs,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()

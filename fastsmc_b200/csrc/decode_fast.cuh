@@ -881,6 +881,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
             const bool closing = now >= 0 && site == scanTo - 1;
             float* park = reinterpret_cast<float*>(betaSlot(slot)) + lane;  // this site's drained beta slot: [k][32]
             if (__any_sync(kFull, ending)) {
+              __syncwarp();  // every lane has read its beta quads: the slot becomes the parking area (racecheck: WAR)
               if (wantAge) {
                 // rare: park the per-state sums (through site-1) for emitSegment
 #pragma unroll
@@ -904,6 +905,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
               }
             }
             if (__any_sync(kFull, closing)) {
+              __syncwarp();
               if (wantAge) {
 #pragma unroll
                 for (int k = 0; k < (ACC ? S : 1); ++k) {

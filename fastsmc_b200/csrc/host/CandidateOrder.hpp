@@ -518,6 +518,54 @@ void groupByKey(const int64_t n, const int numKeys, unsigned threads, KeyFn&& ke
   });
 }
 
+// Seed-map iteration rank of every haplotype's word group, for every word: rank[w * numHaps + h] = position, in the
+// iteration order of the reference's SeedHash map after word w's insertIndividuals calls (ref: FastSMC.cpp:204-206,
+// HASHING/SeedHash.hpp:41-45, 80), of the bucket that holds haplotype h.  Within a word the reference visits buckets in
+// this order and enumerates a bucket's pairs (i < ii) in haplotype order, so (rank, a, b) is the creation order of the
+// word's new match intervals.  The seed map keeps its grown bucket count from word to word (unordered_map::clear), which
+// is the only coupling between words; the words are then independent and run on all host threads.
+template <class WordFn>
+std::vector<uint32_t> seedGroupRanks(const uint32_t numHaps, const int numWords, WordFn&& rawWord, const unsigned threads = 0)
+{
+  std::vector<uint32_t> rank(static_cast<size_t>(std::max(numWords, 0)) * numHaps);
+  if (numWords <= 0) {
+    return rank;
+  }
+  std::vector<size_t> distinct(static_cast<size_t>(numWords), 0);
+  parallelForWords(numWords, threads, [&](const int w) {
+    std::vector<uint64_t> keys(numHaps);
+    for (uint32_t h = 0; h < numHaps; ++h) {
+      keys[h] = rawWord(h, w);
+    }
+    std::sort(keys.begin(), keys.end());
+    distinct[w] = static_cast<size_t>(std::unique(keys.begin(), keys.end()) - keys.begin());
+  });
+  std::vector<size_t> seedBuckets(static_cast<size_t>(numWords), 17);
+  size_t buckets = 17;
+  for (int w = 0; w < numWords; ++w) {
+    seedBuckets[w] = buckets;
+    buckets = NodeOrderMap::bucketsAfter(buckets, distinct[w]);
+  }
+  parallelForWords(numWords, threads, [&](const int w) {
+    NodeOrderMap seeds(seedBuckets[w]);
+    std::vector<int> nodeOfHap(numHaps);
+    for (uint32_t h = 0; h < numHaps; ++h) {
+      bool isNew;
+      nodeOfHap[h] = seeds.insert(rawWord(h, w), 0, isNew);
+    }
+    std::vector<uint32_t> rankOfNode(numHaps, 0);
+    uint32_t r = 0;
+    for (int nd = seeds.first(); nd != NodeOrderMap::kEnd; nd = seeds.next(nd)) {
+      rankOfNode[static_cast<size_t>(nd)] = r++;
+    }
+    uint32_t* out = rank.data() + static_cast<size_t>(w) * numHaps;
+    for (uint32_t h = 0; h < numHaps; ++h) {
+      out[h] = rankOfNode[static_cast<size_t>(nodeOfHap[h])];
+    }
+  });
+  return rank;
+}
+
 template <class Intervals, class WordFn, class LengthFn, class EmitFn>
 void replayReferenceOrderFast(const Intervals& intervals, const uint32_t numHaps, const int numWords,
                               const int gap, WordFn&& rawWord, LengthFn&& longEnough, EmitFn&& emit,

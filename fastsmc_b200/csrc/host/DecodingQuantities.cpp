@@ -2,6 +2,9 @@
 #include "DecodingQuantities.hpp"
 
 #include <cstdlib>
+#include <map>
+#include <memory>
+#include <mutex>
 #include <iostream>
 #include <set>
 #include <sstream>
@@ -15,6 +18,18 @@ DecodingQuantities::DecodingQuantities(const std::string& fileName)
   validateDecodingQuantitiesFile(fileName);
   std::cout << "Using precomputed decoding info from " << fileName << std::endl;
   createFromGzippedText(fileName);
+}
+
+const DecodingQuantities& DecodingQuantities::cached(const std::string& fileName)
+{
+  static std::mutex lock;
+  static std::map<std::string, std::unique_ptr<DecodingQuantities>> table;
+  std::lock_guard<std::mutex> g(lock);
+  auto it = table.find(fileName);
+  if (it == table.end()) {
+    it = table.emplace(fileName, std::make_unique<DecodingQuantities>(fileName)).first;
+  }
+  return *it->second;
 }
 
 // ref: DecodingQuantities.cpp:39-58

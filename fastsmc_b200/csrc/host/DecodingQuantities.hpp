@@ -32,6 +32,9 @@ public:
 
   DecodingQuantities() = default;
   explicit DecodingQuantities(const std::string& fileName);
+  /// The parsed contents of `fileName`, read once per process: the jobs of one data set (runJobs / runAllJobs) all use
+  /// the same table, and parsing its 20-40 MB of gzipped text costs more than a small job's decoding.
+  static const DecodingQuantities& cached(const std::string& fileName);
 
 private:
   void validateDecodingQuantitiesFile(const std::string& fileName);

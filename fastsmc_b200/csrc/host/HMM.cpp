@@ -74,7 +74,8 @@ struct HMM::SegmentBlock {
 };
 
 HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/)
-    : data(std::move(_data)), m_decodingQuant(_decodingParams.decodingQuantFile), decodingParams(_decodingParams)
+    : data(std::move(_data)), m_decodingQuant(DecodingQuantities::cached(_decodingParams.decodingQuantFile)),
+      decodingParams(_decodingParams)
 {
   if (decodingParams.decodingSequence) {
     throw std::runtime_error("sequence mode is not supported by the B200 build (array mode only)");

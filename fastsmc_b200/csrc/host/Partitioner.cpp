@@ -46,33 +46,37 @@ std::vector<int> jobsOfRank(const int jobs, const int world, const int rank)
   return mine;
 }
 
-std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vector<int>& devices)
+std::vector<JobReport> runJobs(const DecodingParams& params, const Data& whole, const std::function<int()>& nextJob,
+                               const std::vector<int>& devices)
 {
   if (devices.empty()) {
-    throw std::runtime_error("runAllJobs: no devices given");
+    throw std::runtime_error("runJobs: no devices given");
   }
-  const std::vector<int> order = jobOrder(params.jobs);
-  std::vector<JobReport> reports(static_cast<size_t>(params.jobs));
-  // the files are read once; every job cuts its two sample windows out of the result (Data::forJob)
-  DecodingParams wholeParams = params;
-  wholeParams.jobs = 1;
-  wholeParams.jobInd = 1;
-  const Data whole(wholeParams);
-  std::atomic<size_t> next{0};
+  std::vector<JobReport> reports;
+  std::mutex lock;  // the job source and the report list
   auto worker = [&](const int device) {
-    for (size_t i = next++; i < order.size(); i = next++) {
-      JobReport& rep = reports[static_cast<size_t>(order[i] - 1)];
-      rep.jobInd = order[i];
+    for (;;) {
+      int jobInd;
+      {
+        std::lock_guard<std::mutex> g(lock);
+        jobInd = nextJob();
+      }
+      if (jobInd < 1 || jobInd > params.jobs) {
+        return;
+      }
+      JobReport rep;
+      rep.jobInd = jobInd;
       rep.device = device;
       const auto t0 = std::chrono::steady_clock::now();
       try {
         DecodingParams p = params;
-        p.jobInd = order[i];
+        p.jobInd = jobInd;
         p.device = device;
         p.verbose = false;
         // reading, model preparation and decoding of different jobs overlap freely: the only process-wide state, the
         // std::rand sequence of the emission preparation, is seeded and consumed under its own lock (Data.cpp)
         auto job = std::make_unique<FastSMC>(p, Data::forJob(whole, p));
+        rep.prepareSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
         job->run();
         const HMM::RunStats& st = job->hmm().getRunStats();
         rep.candidates = job->getSeedingStats().candidates;
@@ -81,10 +85,16 @@ std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vecto
         rep.pairSites = st.pairSites;
         rep.kernelMs = st.kernelMs;
         rep.seedMs = job->getSeedingStats().device.kernelMs;
+        rep.seedSeconds = job->getSeedingStats().seedWallS;
+        rep.orderSeconds = job->getSeedingStats().orderWallS;
+        rep.decodeSeconds = st.decodeWallS;
+        rep.outputSeconds = st.outputWallS;
       } catch (const std::exception& e) {
         rep.error = e.what();
       }
       rep.wallSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+      std::lock_guard<std::mutex> g(lock);
+      reports.push_back(rep);
     }
   };
   std::vector<std::thread> pool;
@@ -95,7 +105,23 @@ std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vecto
   for (auto& t : pool) {
     t.join();
   }
+  std::sort(reports.begin(), reports.end(), [](const JobReport& a, const JobReport& b) { return a.jobInd < b.jobInd; });
   return reports;
+}
+
+std::vector<JobReport> runAllJobs(const DecodingParams& params, const std::vector<int>& devices)
+{
+  if (devices.empty()) {
+    throw std::runtime_error("runAllJobs: no devices given");
+  }
+  const std::vector<int> order = jobOrder(params.jobs);
+  // the files are read once; every job cuts its two sample windows out of the result (Data::forJob)
+  DecodingParams wholeParams = params;
+  wholeParams.jobs = 1;
+  wholeParams.jobInd = 1;
+  const Data whole(wholeParams);
+  size_t next = 0;
+  return runJobs(params, whole, [&] { return next < order.size() ? order[next++] : 0; }, devices);
 }
 
 }  // namespace ASMC

@@ -11,9 +11,11 @@
 // different jobs is therefore serialised under a mutex (it is the same sequence for every job), decoding is not.
 #pragma once
 
+#include <functional>
 #include <string>
 #include <vector>
 
+#include "Data.hpp"
 #include "DecodingParams.hpp"
 
 namespace ASMC
@@ -27,6 +29,9 @@ struct JobReport {
   double kernelMs = 0.0;   // device time in the decode kernels
   double seedMs = 0.0;     // device time in the seeding kernels
   double wallSeconds = 0.0;
+  // host wall time of the job's stages: cutting the job's samples out of the data set + model tables + upload,
+  // fsmc_seed, candidate order, fsmc_decode calls, record formatting/compression
+  double prepareSeconds = 0.0, seedSeconds = 0.0, orderSeconds = 0.0, decodeSeconds = 0.0, outputSeconds = 0.0;
   std::string error;       // empty on success
 };
 
@@ -36,6 +41,12 @@ std::vector<int> jobOrder(int jobs);
 // Static split used when every rank is its own process (torchrun): the jobs of `rank` out of `world`, dealt round-robin
 // over jobOrder(jobs).
 std::vector<int> jobsOfRank(int jobs, int world, int rank);
+
+// Runs the jobs that `nextJob` hands out (a job index in 1..params.jobs, or 0 when none is left; called under a lock)
+// on `devices`, one host thread per entry, every job cut out of `whole` (the data set read with jobs = 1).  This is
+// what a torchrun rank calls with a counter shared by all ranks as the job source.
+std::vector<JobReport> runJobs(const DecodingParams& params, const Data& whole, const std::function<int()>& nextJob,
+                               const std::vector<int>& devices);
 
 // Runs jobs 1..params.jobs of the data set on `devices` (CUDA ordinals; a device may appear twice to run two host
 // threads on it).  params.jobInd is ignored.  Returns one report per job, ordered by jobInd.

@@ -1,5 +1,6 @@
 // pyASMC — Python bindings with the reference's class, method and keyword names
 // (ref: ASMC_SRC/SRC/pybind.cpp:54-252).  Matrices are exposed as numpy arrays instead of Eigen casters.
+#include <pybind11/functional.h>
 #include <pybind11/numpy.h>
 #include <pybind11/pybind11.h>
 #include <pybind11/stl.h>
@@ -389,10 +390,17 @@ PYBIND11_MODULE(pyASMC, m)
       .def_readonly("kernelMs", &ASMC::JobReport::kernelMs)
       .def_readonly("seedMs", &ASMC::JobReport::seedMs)
       .def_readonly("wallSeconds", &ASMC::JobReport::wallSeconds)
+      .def_readonly("prepareSeconds", &ASMC::JobReport::prepareSeconds)
+      .def_readonly("seedSeconds", &ASMC::JobReport::seedSeconds)
+      .def_readonly("orderSeconds", &ASMC::JobReport::orderSeconds)
+      .def_readonly("decodeSeconds", &ASMC::JobReport::decodeSeconds)
+      .def_readonly("outputSeconds", &ASMC::JobReport::outputSeconds)
       .def_readonly("error", &ASMC::JobReport::error);
   m.def("jobOrder", &ASMC::jobOrder, "jobs"_a);
   m.def("jobsOfRank", &ASMC::jobsOfRank, "jobs"_a, "world"_a, "rank"_a);
   m.def("runAllJobs", &ASMC::runAllJobs, "params"_a, "devices"_a, py::call_guard<py::gil_scoped_release>());
+  // the job source is a Python callable (e.g. a counter shared by torchrun ranks); pybind re-acquires the GIL to call it
+  m.def("runJobs", &ASMC::runJobs, "params"_a, "whole"_a, "nextJob"_a, "devices"_a, py::call_guard<py::gil_scoped_release>());
 
   // host-only pieces, callable without a GPU (used by the CPU test-suite)
   m.def(
@@ -402,6 +410,20 @@ PYBIND11_MODULE(pyASMC, m)
         return tablesToDict(HMM::buildModelTables(data, dq, params), dq);
       },
       "data"_a, "params"_a);
+  m.def(
+      "seedGroupRanks",
+      [](const Data& data) {
+        const uint32_t H = static_cast<uint32_t>(data.numLoadedHaplotypes());
+        const int W = data.sites / 64;
+        auto rawWord = [&](uint32_t h, int w) {
+          return data.hapBits[static_cast<size_t>(h) * data.wordsPerHap + w] ^ data.flipMask[w];
+        };
+        const std::vector<uint32_t> r = candidate_order::seedGroupRanks(H, W, rawWord);
+        py::array_t<uint32_t> out({static_cast<py::ssize_t>(W), static_cast<py::ssize_t>(H)});
+        std::copy(r.begin(), r.end(), out.mutable_data());
+        return out;
+      },
+      "data"_a);
   m.def(
       "replayReferenceOrder",
       [](py::array_t<int64_t, py::array::c_style | py::array::forcecast> intervals, const Data& data, int gap,

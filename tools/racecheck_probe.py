@@ -42,7 +42,7 @@ def main():
     os.makedirs("/tmp/fsmc_racecheck", exist_ok=True)
     root = "/tmp/fsmc_racecheck/syn"
     if not os.path.exists(root + ".hap.gz"):
-        synth.dataset(root, 64, 640, 2_000_000, 1, 99)
+        synth.dataset(root, 320, 640, 2_000_000, 1, 99)
     rng = np.random.default_rng(1)
     n_pairs = 5 * 32 + 7
     for label, r, dq, conditional, env in (
