@@ -16,6 +16,8 @@
 #include "decode_kernels.cuh"
 #include "decode_fast.cuh"
 #include "seed_kernels.cuh"
+#include "seed_order.h"
+#include "host/SeedMapOrder.hpp"
 #include "segment_sort.h"
 #include "split_select.h"
 
@@ -106,8 +108,7 @@ struct fsmc_plan;
 struct SeedKey {
   int32_t gap;
   float minLengthCm;
-  const void* geneticPositions;
-  const void* globalHapId;
+  uint64_t genPosSum, globalIdSum, flipSum;  // checksums of the callers' arrays (contents, not addresses)
   uint32_t window[4];
   int32_t lastJob, aboveDiag;
   uint32_t flags;
@@ -133,6 +134,9 @@ struct fsmc_ctx {
   DevBuf<unsigned long long> seedGroupPairBase, seedCounters, seedWordCounters, seedChunkBase;
   DevBuf<float> seedGenPos;
   DevBuf<fsmc_match> seedOut;
+  DevBuf<uint32_t> seedRank;              // [W][H] seed-map iteration ranks (FSMC_SEED_REFERENCE_ORDER)
+  fsmc::CandidateOrderer orderer;         // device-side reference candidate order (seed_order.h)
+  const fsmc_match* orderedOut = nullptr; // its result, valid until the next fsmc_seed call
   bool seedCacheValid = false;  // seedOut holds every interval of the last fsmc_seed call (which overflowed the caller)
   SeedKey seedCacheKey{};
   fsmc_seed_stats seedCacheStats{};
@@ -889,14 +893,25 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   const uint32_t H = static_cast<uint32_t>(ctx->numHaps);
   const int L = static_cast<int>(ctx->sites);
   const int W = L / 64;  // a trailing partial word is never hashed
-  // A call that overflowed the caller's buffer leaves its intervals on the device; the retry with a larger buffer and
-  // the same parameters only copies them out.
+  const bool refOrder = sp->flags & FSMC_SEED_REFERENCE_ORDER;
+  // A call that overflowed the caller's buffer leaves its result on the device; the retry with a larger buffer and the
+  // same inputs only copies it out.  "Same inputs" = same scalar parameters and same CONTENTS of the two arrays (a
+  // checksum, not their addresses: a caller may reuse a buffer for other data).
+  auto checksum = [](const void* p, const size_t bytes) {
+    uint64_t h = 1469598103934665603ull;
+    const unsigned char* c = static_cast<const unsigned char*>(p);
+    for (size_t i = 0; i < bytes; ++i) {
+      h = (h ^ c[i]) * 1099511628211ull;
+    }
+    return h;
+  };
   SeedKey key;
   std::memset(&key, 0, sizeof key);
   key.gap = sp->gap;
   key.minLengthCm = sp->minLengthCm;
-  key.geneticPositions = sp->geneticPositions;
-  key.globalHapId = sp->globalHapId;
+  key.genPosSum = checksum(sp->geneticPositions, sizeof(float) * static_cast<size_t>(L));
+  key.globalIdSum = checksum(sp->globalHapId, sizeof(uint32_t) * H);
+  key.flipSum = (refOrder && sp->flipMask) ? checksum(sp->flipMask, sizeof(uint64_t) * static_cast<size_t>(std::max(W, 0))) : 0;
   key.window[0] = sp->loI;
   key.window[1] = sp->hiI;
   key.window[2] = sp->loJ;
@@ -907,116 +922,159 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   const bool cacheHit = ctx->seedCacheValid && std::memcmp(&key, &ctx->seedCacheKey, sizeof key) == 0 &&
                         capacity >= ctx->seedCacheStats.numMatches;
   if (!cacheHit) {
-  ctx->seedCacheValid = false;
-  uint32_t C = 64;
-  while (C < 2u * H) {
-    C <<= 1;
-  }
-  const size_t maxGroups = H / 2 + 2;
-  // Words are independent, so a launch handles a batch of them (blockIdx.y = word in the batch), each with its own
-  // slice of the scratch tables: at small sample counts the per-word kernels are a few microseconds of work and the
-  // pass would otherwise be bound by launch latency (5 launches per word).  The batch is as large as 2 GiB of tables
-  // allow, up to 64 words.
-  const size_t perWordBytes = static_cast<size_t>(C) * 12 + static_cast<size_t>(H) * 12 + maxGroups * 16 + 40;
-  const int WB = static_cast<int>(std::max<size_t>(1, std::min<size_t>({64, static_cast<size_t>(std::max(W, 1)),
-                                                                       (size_t{2} << 30) / perWordBytes})));
-  FSMC_CUDA(ctx->seedKeysT.ensure(static_cast<size_t>(std::max(W, 1)) * H));
-  FSMC_CUDA(ctx->seedOwner.ensure(static_cast<size_t>(WB) * C));
-  FSMC_CUDA(ctx->seedSlotCount.ensure(static_cast<size_t>(WB) * C));
-  FSMC_CUDA(ctx->seedSlotGroup.ensure(static_cast<size_t>(WB) * C));
-  FSMC_CUDA(ctx->seedSlotOf.ensure(static_cast<size_t>(WB) * H));
-  FSMC_CUDA(ctx->seedRankOf.ensure(static_cast<size_t>(WB) * H));
-  FSMC_CUDA(ctx->seedMembers.ensure(static_cast<size_t>(WB) * H));
-  FSMC_CUDA(ctx->seedGroupSize.ensure(static_cast<size_t>(WB) * maxGroups));
-  FSMC_CUDA(ctx->seedGroupMemberBase.ensure(static_cast<size_t>(WB) * maxGroups));
-  FSMC_CUDA(ctx->seedGroupPairBase.ensure(static_cast<size_t>(WB) * (maxGroups + 1)));
-  FSMC_CUDA(ctx->seedWordCounters.ensure(static_cast<size_t>(WB) * 4));
-  FSMC_CUDA(ctx->seedChunkBase.ensure(static_cast<size_t>(WB) + 2));
-  FSMC_CUDA(ctx->seedCounters.ensure(8));
-  FSMC_CUDA(ctx->seedGenPos.ensure(L));
-  FSMC_CUDA(ctx->seedGlobalId.ensure(H));
-  // device-side interval buffer: at least 16 Mi intervals (256 MiB) whatever the caller's capacity, so that an
-  // under-sized first call does not have to be recomputed
-  size_t freeB = 0, totalB = 0;
-  FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
-  const long long devCap = std::max<long long>(
-      capacity, std::min<long long>(1ll << 24, static_cast<long long>((freeB + ctx->seedOut.n * sizeof(fsmc_match)) / 4 /
-                                                                       sizeof(fsmc_match))));
-  FSMC_CUDA(ctx->seedOut.ensure(static_cast<size_t>(devCap)));
-  FSMC_CUDA(cudaMemcpyAsync(ctx->seedGenPos.p, sp->geneticPositions, sizeof(float) * L, cudaMemcpyHostToDevice, st));
-  FSMC_CUDA(cudaMemcpyAsync(ctx->seedGlobalId.p, sp->globalHapId, sizeof(uint32_t) * H, cudaMemcpyHostToDevice, st));
-  FSMC_CUDA(cudaMemsetAsync(ctx->seedCounters.p, 0, 8 * sizeof(unsigned long long), st));
-
-  fsmc::SeedArgs a{};
-  a.haps = ctx->haps.p;
-  a.wordsPerHap = ctx->model.wordsPerHap;
-  a.keysT = ctx->seedKeysT.p;
-  a.H = H;
-  a.W = W;
-  a.L = L;
-  a.gap = sp->gap;
-  a.minLengthCm = sp->minLengthCm;
-  a.genPos = ctx->seedGenPos.p;
-  a.globalId = ctx->seedGlobalId.p;
-  a.loI = sp->loI;
-  a.hiI = sp->hiI;
-  a.loJ = sp->loJ;
-  a.hiJ = sp->hiJ;
-  a.lastJob = sp->lastJob;
-  a.aboveDiag = sp->aboveDiag;
-  a.flags = sp->flags;
-  a.owner = ctx->seedOwner.p;
-  a.slotCount = ctx->seedSlotCount.p;
-  a.slotGroup = ctx->seedSlotGroup.p;
-  a.C = C;
-  a.slotOf = ctx->seedSlotOf.p;
-  a.rankOf = ctx->seedRankOf.p;
-  a.groupSize = ctx->seedGroupSize.p;
-  a.groupMemberBase = ctx->seedGroupMemberBase.p;
-  a.groupPairBase = ctx->seedGroupPairBase.p;
-  a.members = ctx->seedMembers.p;
-  a.maxGroups = static_cast<uint32_t>(maxGroups);
-  a.wordCounters = ctx->seedWordCounters.p;
-  a.batchChunkBase = ctx->seedChunkBase.p;
-  a.counters = ctx->seedCounters.p;
-  a.out = ctx->seedOut.p;
-  a.capacity = devCap;
-
-  int launches = 0;
-  FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
-  const int sms = ctx->prop.multiProcessorCount;
-  if (W > 0) {
-    const dim3 tb(32, 8), tg((H + 31) / 32, (W + 31) / 32);
-    fsmc::transposeWordsKernel<<<tg, tb, 0, st>>>(a.haps, a.wordsPerHap, H, W, ctx->seedKeysT.p);
-    ++launches;
-    for (int w0 = 0; w0 < W; w0 += WB) {
-      const unsigned nw = static_cast<unsigned>(std::min(WB, W - w0));
-      // grid.x: enough CTAs per word to cover it, but no more than ~8 CTAs per SM over the whole batch
-      const long long perWordCap = std::max<long long>(1, sms * 8ll / nw);
-      const unsigned hapBlocks = static_cast<unsigned>(std::min<long long>((H + 255ll) / 256, perWordCap));
-      const unsigned slotBlocks = static_cast<unsigned>(std::min<long long>((C + 255ll) / 256, perWordCap));
-      a.wordBase = w0;
-      a.wordsInBatch = static_cast<int>(nw);
-      FSMC_CUDA(cudaMemsetAsync(a.owner, 0, sizeof(uint32_t) * C * nw, st));
-      FSMC_CUDA(cudaMemsetAsync(a.slotCount, 0, sizeof(uint32_t) * C * nw, st));
-      FSMC_CUDA(cudaMemsetAsync(a.wordCounters, 0, sizeof(unsigned long long) * 4 * nw, st));
-      fsmc::groupInsertKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
-      fsmc::groupCompactKernel<<<dim3(slotBlocks, nw), 256, 0, st>>>(a);
-      fsmc::groupScanKernel<<<nw, 1024, 0, st>>>(a);
-      fsmc::groupScatterKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
-      fsmc::batchChunksKernel<<<1, 32, 0, st>>>(a);
-      fsmc::pairExtendKernel<<<sms * 8, fsmc::kPairBlockThreads, 0, st>>>(a);
-      launches += 6;
+    ctx->seedCacheValid = false;
+    ctx->orderedOut = nullptr;
+    uint32_t C = 64;
+    while (C < 2u * H) {
+      C <<= 1;
     }
-    FSMC_CUDA(cudaGetLastError());
-  }
-  FSMC_CUDA(cudaEventRecord(ctx->ev[2], st));
-  unsigned long long counters[8] = {0};
-  FSMC_CUDA(cudaMemcpyAsync(counters, ctx->seedCounters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
-  FSMC_CUDA(cudaStreamSynchronize(st));
-  {
+    const size_t maxGroups = H / 2 + 2;
+    // Words are independent, so a launch handles a batch of them (blockIdx.y = word in the batch), each with its own
+    // slice of the scratch tables: at small sample counts the per-word kernels are a few microseconds of work and the
+    // pass would otherwise be bound by launch latency (5 launches per word).  The batch is as large as 2 GiB of tables
+    // allow, up to 64 words.
+    const size_t perWordBytes = static_cast<size_t>(C) * 12 + static_cast<size_t>(H) * 12 + maxGroups * 16 + 40;
+    const int WB = static_cast<int>(std::max<size_t>(1, std::min<size_t>({64, static_cast<size_t>(std::max(W, 1)),
+                                                                         (size_t{2} << 30) / perWordBytes})));
+    FSMC_CUDA(ctx->seedKeysT.ensure(static_cast<size_t>(std::max(W, 1)) * H));
+    FSMC_CUDA(ctx->seedOwner.ensure(static_cast<size_t>(WB) * C));
+    FSMC_CUDA(ctx->seedSlotCount.ensure(static_cast<size_t>(WB) * C));
+    FSMC_CUDA(ctx->seedSlotGroup.ensure(static_cast<size_t>(WB) * C));
+    FSMC_CUDA(ctx->seedSlotOf.ensure(static_cast<size_t>(WB) * H));
+    FSMC_CUDA(ctx->seedRankOf.ensure(static_cast<size_t>(WB) * H));
+    FSMC_CUDA(ctx->seedMembers.ensure(static_cast<size_t>(WB) * H));
+    FSMC_CUDA(ctx->seedGroupSize.ensure(static_cast<size_t>(WB) * maxGroups));
+    FSMC_CUDA(ctx->seedGroupMemberBase.ensure(static_cast<size_t>(WB) * maxGroups));
+    FSMC_CUDA(ctx->seedGroupPairBase.ensure(static_cast<size_t>(WB) * (maxGroups + 1)));
+    FSMC_CUDA(ctx->seedWordCounters.ensure(static_cast<size_t>(WB) * 4));
+    FSMC_CUDA(ctx->seedChunkBase.ensure(static_cast<size_t>(WB) + 2));
+    FSMC_CUDA(ctx->seedCounters.ensure(8));
+    FSMC_CUDA(ctx->seedGenPos.ensure(L));
+    FSMC_CUDA(ctx->seedGlobalId.ensure(H));
+    // device-side interval buffer: at least 16 Mi intervals (256 MiB) whatever the caller's capacity, so that an
+    // under-sized first call does not have to be recomputed.  In reference-order mode every interval of the job is
+    // needed on the device (the caller's capacity only counts candidates): an eighth of the free memory to begin with.
+    size_t freeB = 0, totalB = 0;
+    FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const long long avail = static_cast<long long>((freeB + ctx->seedOut.n * sizeof(fsmc_match)) / sizeof(fsmc_match));
+    long long devCap = refOrder ? std::max<long long>(1ll << 20, std::min<long long>(avail / 8, 0x7ffffff0ll))
+                                : std::max<long long>(capacity, std::min<long long>(1ll << 24, avail / 4));
+    FSMC_CUDA(ctx->seedOut.ensure(static_cast<size_t>(devCap)));
+    FSMC_CUDA(cudaMemcpyAsync(ctx->seedGenPos.p, sp->geneticPositions, sizeof(float) * L, cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaMemcpyAsync(ctx->seedGlobalId.p, sp->globalHapId, sizeof(uint32_t) * H, cudaMemcpyHostToDevice, st));
+
+    fsmc::SeedArgs a{};
+    a.haps = ctx->haps.p;
+    a.wordsPerHap = ctx->model.wordsPerHap;
+    a.keysT = ctx->seedKeysT.p;
+    a.H = H;
+    a.W = W;
+    a.L = L;
+    a.gap = sp->gap;
+    a.minLengthCm = sp->minLengthCm;
+    a.genPos = ctx->seedGenPos.p;
+    a.globalId = ctx->seedGlobalId.p;
+    a.loI = sp->loI;
+    a.hiI = sp->hiI;
+    a.loJ = sp->loJ;
+    a.hiJ = sp->hiJ;
+    a.lastJob = sp->lastJob;
+    a.aboveDiag = sp->aboveDiag;
+    a.flags = sp->flags | (refOrder ? FSMC_SEED_ALL_INTERVALS : 0u);
+    a.owner = ctx->seedOwner.p;
+    a.slotCount = ctx->seedSlotCount.p;
+    a.slotGroup = ctx->seedSlotGroup.p;
+    a.C = C;
+    a.slotOf = ctx->seedSlotOf.p;
+    a.rankOf = ctx->seedRankOf.p;
+    a.groupSize = ctx->seedGroupSize.p;
+    a.groupMemberBase = ctx->seedGroupMemberBase.p;
+    a.groupPairBase = ctx->seedGroupPairBase.p;
+    a.members = ctx->seedMembers.p;
+    a.maxGroups = static_cast<uint32_t>(maxGroups);
+    a.wordCounters = ctx->seedWordCounters.p;
+    a.batchChunkBase = ctx->seedChunkBase.p;
+    a.counters = ctx->seedCounters.p;
+
+    int launches = 0;
+    FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
+    const int sms = ctx->prop.multiProcessorCount;
+    if (W > 0) {
+      const dim3 tb(32, 8), tg((H + 31) / 32, (W + 31) / 32);
+      fsmc::transposeWordsKernel<<<tg, tb, 0, st>>>(a.haps, a.wordsPerHap, H, W, ctx->seedKeysT.p);
+      ++launches;
+    }
+    // reference order: the seed map's iteration ranks (host threads, SeedMapOrder.hpp) are computed from the transposed
+    // words while the device runs the pair kernels
+    std::vector<uint64_t> hostKeys;
+    std::vector<uint32_t> hostRank;
+    std::thread rankThread;
+    double rankMs = 0.0;
+    if (refOrder && W > 0) {
+      hostKeys.resize(static_cast<size_t>(W) * H);
+      FSMC_CUDA(cudaMemcpyAsync(hostKeys.data(), ctx->seedKeysT.p, hostKeys.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
+      FSMC_CUDA(cudaStreamSynchronize(st));
+      const uint64_t* flip = sp->flipMask;
+      rankThread = std::thread([&hostKeys, &hostRank, &rankMs, flip, H, W] {
+        const auto t0 = std::chrono::steady_clock::now();
+        hostRank = candidate_order::seedGroupRanks(
+            H, W, [&](const uint32_t h, const int w) { return hostKeys[static_cast<size_t>(w) * H + h] ^ (flip ? flip[w] : 0ull); });
+        rankMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+      });
+    }
+    struct Joiner {
+      std::thread& t;
+      ~Joiner()
+      {
+        if (t.joinable()) {
+          t.join();
+        }
+      }
+    } joiner{rankThread};
+    unsigned long long counters[8] = {0};
+    for (int attempt = 0; attempt < 2; ++attempt) {
+      a.out = ctx->seedOut.p;
+      a.capacity = devCap;
+      FSMC_CUDA(cudaMemsetAsync(ctx->seedCounters.p, 0, 8 * sizeof(unsigned long long), st));
+      for (int w0 = 0; w0 < W; w0 += WB) {
+        const unsigned nw = static_cast<unsigned>(std::min(WB, W - w0));
+        // grid.x: enough CTAs per word to cover it, but no more than ~8 CTAs per SM over the whole batch
+        const long long perWordCap = std::max<long long>(1, sms * 8ll / nw);
+        const unsigned hapBlocks = static_cast<unsigned>(std::min<long long>((H + 255ll) / 256, perWordCap));
+        const unsigned slotBlocks = static_cast<unsigned>(std::min<long long>((C + 255ll) / 256, perWordCap));
+        a.wordBase = w0;
+        a.wordsInBatch = static_cast<int>(nw);
+        FSMC_CUDA(cudaMemsetAsync(a.owner, 0, sizeof(uint32_t) * C * nw, st));
+        FSMC_CUDA(cudaMemsetAsync(a.slotCount, 0, sizeof(uint32_t) * C * nw, st));
+        FSMC_CUDA(cudaMemsetAsync(a.wordCounters, 0, sizeof(unsigned long long) * 4 * nw, st));
+        fsmc::groupInsertKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
+        fsmc::groupCompactKernel<<<dim3(slotBlocks, nw), 256, 0, st>>>(a);
+        fsmc::groupScanKernel<<<nw, 1024, 0, st>>>(a);
+        fsmc::groupScatterKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
+        fsmc::batchChunksKernel<<<1, 32, 0, st>>>(a);
+        fsmc::pairExtendKernel<<<sms * 8, fsmc::kPairBlockThreads, 0, st>>>(a);
+        launches += 6;
+      }
+      FSMC_CUDA(cudaGetLastError());
+      FSMC_CUDA(cudaMemcpyAsync(counters, ctx->seedCounters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+      FSMC_CUDA(cudaStreamSynchronize(st));
+      if (!refOrder || static_cast<long long>(counters[3]) <= devCap) {
+        break;
+      }
+      // reference order needs every interval on the device: run the pass again with a buffer of the right size
+      devCap = static_cast<long long>(counters[3]) + 1024;
+      if (devCap >= 0x7fffffffll) {
+        return fail(FSMC_E_NOMEM, "fsmc_seed: %llu intervals in one job exceed the 2^31 limit of the device ordering; use more jobs",
+                    counters[3]);
+      }
+      FSMC_CUDA(ctx->seedOut.ensure(static_cast<size_t>(devCap)));
+    }
+    FSMC_CUDA(cudaEventRecord(ctx->ev[2], st));
+    FSMC_CUDA(cudaStreamSynchronize(st));
     fsmc_seed_stats& cs = ctx->seedCacheStats;
+    cs = fsmc_seed_stats{};
     cs.numMatches = static_cast<int64_t>(counters[3]);
+    cs.numIntervals = cs.numMatches;
     cs.pairVisits = static_cast<int64_t>(counters[4]);
     cs.numStarts = static_cast<int64_t>(counters[5]);
     cs.numWords = W;
@@ -1027,9 +1085,33 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
     // and probed; three per-haplotype bookkeeping words; 16 bytes per emitted interval
     cs.bytesRead = static_cast<int64_t>(W) * (static_cast<int64_t>(H) * (8 + 8 + 8 + 12) + static_cast<int64_t>(C) * 12) +
                    16 * cs.numMatches;
+    if (refOrder) {
+      if (rankThread.joinable()) {
+        rankThread.join();
+      }
+      cs.rankHostMs = static_cast<float>(rankMs);
+      FSMC_CUDA(ctx->seedRank.ensure(std::max<size_t>(hostRank.size(), 1)));
+      if (!hostRank.empty()) {
+        FSMC_CUDA(cudaMemcpyAsync(ctx->seedRank.p, hostRank.data(), hostRank.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, st));
+      }
+      fsmc::OrderStats os;
+      long long numCandidates = 0;
+      const cudaError_t e = ctx->orderer.order(ctx->seedOut.p, static_cast<long long>(counters[3]), H, W, L, sp->gap, sp->minLengthCm,
+                                               ctx->seedGenPos.p, ctx->seedRank.p, st, &ctx->orderedOut, &numCandidates, &os);
+      if (e != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e == cudaErrorMemoryAllocation ? FSMC_E_NOMEM : FSMC_E_CUDA, "fsmc_seed: device candidate ordering failed: %s",
+                    cudaGetErrorString(e));
+      }
+      cs.numMatches = numCandidates;
+      cs.maxLiveNodes = os.maxLive;
+      cs.orderEpochs = os.epochs;
+      cs.orderMs = os.deviceMs;
+      ctx->seedCacheValid = true;
+    } else {
+      ctx->seedCacheValid = cs.numMatches <= devCap;  // everything found is on the device
+    }
     ctx->seedCacheKey = key;
-    ctx->seedCacheValid = cs.numMatches <= devCap;  // everything found is on the device
-  }
   }  // !cacheHit
   const long long found = static_cast<long long>(ctx->seedCacheStats.numMatches);
   if (stats) {
@@ -1040,7 +1122,10 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   }
   ctx->seedCacheValid = false;  // consumed by this call
   const long long stored = found;
-  if (stored > 0 && (sp->flags & FSMC_SEED_UNSORTED)) {
+  if (stored > 0 && refOrder) {
+    FSMC_CUDA(cudaMemcpyAsync(out, ctx->orderedOut, stored * sizeof(fsmc_match), cudaMemcpyDeviceToHost, st));
+    FSMC_CUDA(cudaStreamSynchronize(st));
+  } else if (stored > 0 && (sp->flags & FSMC_SEED_UNSORTED)) {
     FSMC_CUDA(cudaMemcpyAsync(out, ctx->seedOut.p, stored * sizeof(fsmc_match), cudaMemcpyDeviceToHost, st));
     FSMC_CUDA(cudaStreamSynchronize(st));
     for (long long i = 0; i < stored; ++i) {

@@ -3,6 +3,7 @@
 
 #include <algorithm>
 #include <chrono>
+#include <cstdlib>
 #include <iostream>
 #include <stdexcept>
 
@@ -70,8 +71,14 @@ void ASMC::FastSMC::seedAndDecode()
   sp.hiJ = mData.w_j * mData.windowSize;
   sp.lastJob = lastJob;
   sp.aboveDiag = mData.is_j_above_diag;
-  // the order replay groups the intervals itself: no need for the canonical sort
-  sp.flags = mParams.referenceCandidateOrder ? (FSMC_SEED_ALL_INTERVALS | FSMC_SEED_UNSORTED) : 0u;
+  // Reference candidate order (the default): computed on the device inside fsmc_seed, which then returns the candidates
+  // only, in decodeFromHashing call order.  FSMC_HOST_ORDER=1 selects the round-1 host replay of the same order
+  // (CandidateOrder.hpp; development / A-B checks): every interval comes back and is replayed on the host threads.
+  static const bool hostOrder = std::getenv("FSMC_HOST_ORDER") != nullptr;
+  const bool deviceOrder = mParams.referenceCandidateOrder && !hostOrder;
+  sp.flipMask = mData.flipMask.data();
+  sp.flags = deviceOrder ? FSMC_SEED_REFERENCE_ORDER
+                         : (mParams.referenceCandidateOrder ? (FSMC_SEED_ALL_INTERVALS | FSMC_SEED_UNSORTED) : 0u);
 
   // not zero-filled: at biobank density the intervals are gigabytes, written once by the copy from the device
   candidate_order::RawArray<fsmc_match> buffer(std::max<size_t>(1u << 16, static_cast<size_t>(H) * 8));
@@ -107,10 +114,13 @@ void ASMC::FastSMC::seedAndDecode()
       mCandidates.push_back(fsmc_match{m.hapA, m.hapB, static_cast<int32_t>(from), static_cast<int32_t>(to)});
     }
   };
-  if (!mParams.referenceCandidateOrder) {
+  if (!mParams.referenceCandidateOrder || deviceOrder) {
+    const double t1 = now();
     for (size_t i = 0; i < found.size(); ++i) {
       submit(found[i]);
     }
+    mSeedStats.submitWallS = now() - t1;
+    mSeedStats.orderWallS = deviceOrder ? mSeedStats.device.orderMs / 1e3 : 0.0;
   } else {
     const double t1 = now();
     auto rawWord = [&](const uint32_t h, const int w) {

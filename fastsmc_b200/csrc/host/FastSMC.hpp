@@ -32,7 +32,8 @@ public:
   struct SeedingStats {
     fsmc_seed_stats device{};
     double seedWallS = 0.0;   // fsmc_seed call
-    double orderWallS = 0.0;  // host replay of the reference candidate order (0 in canonical mode)
+    double orderWallS = 0.0;  // reference candidate order: device passes inside fsmc_seed, or the host replay (FSMC_HOST_ORDER)
+    double submitWallS = 0.0; // decodeFromHashing calls of the ordered candidates (batching + decode submission)
     unsigned long candidates = 0;
   };
   const SeedingStats& getSeedingStats() const { return mSeedStats; }

@@ -328,11 +328,17 @@ PYBIND11_MODULE(pyASMC, m)
       .def_readonly("numWords", &fsmc_seed_stats::numWords)
       .def_readonly("kernelLaunches", &fsmc_seed_stats::kernelLaunches)
       .def_readonly("kernelMs", &fsmc_seed_stats::kernelMs)
-      .def_readonly("bytesRead", &fsmc_seed_stats::bytesRead);
+      .def_readonly("bytesRead", &fsmc_seed_stats::bytesRead)
+      .def_readonly("numIntervals", &fsmc_seed_stats::numIntervals)
+      .def_readonly("maxLiveNodes", &fsmc_seed_stats::maxLiveNodes)
+      .def_readonly("orderEpochs", &fsmc_seed_stats::orderEpochs)
+      .def_readonly("orderMs", &fsmc_seed_stats::orderMs)
+      .def_readonly("rankHostMs", &fsmc_seed_stats::rankHostMs);
   py::class_<ASMC::FastSMC::SeedingStats>(m, "SeedingStats")
       .def_readonly("device", &ASMC::FastSMC::SeedingStats::device)
       .def_readonly("seedWallS", &ASMC::FastSMC::SeedingStats::seedWallS)
       .def_readonly("orderWallS", &ASMC::FastSMC::SeedingStats::orderWallS)
+      .def_readonly("submitWallS", &ASMC::FastSMC::SeedingStats::submitWallS)
       .def_readonly("candidates", &ASMC::FastSMC::SeedingStats::candidates);
 
   py::class_<ASMC::FastSMC>(m, "FastSMC")

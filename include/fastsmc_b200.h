@@ -204,6 +204,13 @@ int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan);
  * ------------------------------------------------------------------------------------------------ */
 #define FSMC_SEED_ALL_INTERVALS 0x1u /* keep intervals shorter than minLengthCm too (order replay)  */
 #define FSMC_SEED_UNSORTED 0x2u      /* skip the canonical sort: intervals in no particular order     */
+/* FSMC_SEED_REFERENCE_ORDER: output = the candidates only (length >= minLengthCm), in the order in which the
+ * reference's FastSMC::run hands them to HMM::decodeFromHashing, i.e. the iteration order of its SeedHash /
+ * ExtendHash maps (boost::unordered_map 1.75; HASHING/SeedHash.hpp:34,80, HASHING/ExtendHash.hpp:29,85-116).  Batch
+ * composition, decode windows and therefore segment boundaries depend on this order (HMM.cpp:561-565, 1199-1204).
+ * Computed on the device (csrc/seed_order.h).  The seed map is keyed by words of RAW alleles: give flipMask when the
+ * haplotypes of fsmc_set_haplotypes are minor-allele folded.                                                        */
+#define FSMC_SEED_REFERENCE_ORDER 0x4u
 
 typedef struct fsmc_match {
   uint32_t hapA;      /* smaller local haplotype index                                            */
@@ -222,6 +229,9 @@ typedef struct fsmc_seed_params {
   int32_t lastJob;                /* jobInd == jobs: open-ended windows, strictly below diagonal  */
   int32_t aboveDiag;              /* Data::is_j_above_diag                                        */
   uint32_t flags;
+  /* [sites/64] (host) bit s%64 of word s/64 = site s was flipped by folding: raw word = word ^ flipMask[w].
+   * NULL = the haplotypes are raw.  Only read with FSMC_SEED_REFERENCE_ORDER.                      */
+  const uint64_t* flipMask;
 } fsmc_seed_params;
 
 typedef struct fsmc_seed_stats {
@@ -232,6 +242,12 @@ typedef struct fsmc_seed_stats {
   int32_t kernelLaunches;
   float kernelMs;         /* device time of the seeding kernels                                    */
   int64_t bytesRead;      /* algorithmic HBM bytes: every word once + grouping traffic             */
+  /* FSMC_SEED_REFERENCE_ORDER: numMatches counts the candidates; every interval is a node of the reference's map */
+  int64_t numIntervals;   /* intervals of any length                                               */
+  int64_t maxLiveNodes;   /* most nodes in the reference's extend map at once                       */
+  int32_t orderEpochs;    /* rehashes of that map + 1                                               */
+  float orderMs;          /* device time of the ordering passes                                     */
+  float rankHostMs;       /* host time of the seed-map iteration ranks (overlaps the seeding kernels) */
 } fsmc_seed_stats;
 
 int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* params, fsmc_match* out, int64_t capacity,

@@ -277,3 +277,89 @@ def test_pipelined_decode_workers_give_the_same_file(asmc, tmp_path, monkeypatch
             texts[workers, hashing] = _lines(f"{p.outFileRoot}.{p.jobInd}.{p.jobs}.FastSMC.ibd.gz")
     for hashing in (True, False):
         assert len(texts["1", hashing]) > 100 and texts["1", hashing] == texts["2", hashing]
+
+
+# ---- reference candidate order computed on the device (csrc/seed_order.cu), synthetic data ------------------------------
+
+
+def _synthetic_params(asmc, root, out, dq, **kw):
+    p = asmc.DecodingParams()
+    p.verbose = False
+    p.inFileRoot, p.decodingQuantFile, p.outFileRoot = root, dq, out
+    p.decodingModeString, p.foldData, p.usingCSFS, p.FastSMC, p.hashing = "array", True, True, True, True
+    for k, v in dict(REGRESSION_PARAMS, **kw).items():
+        setattr(p, k, v)
+    p.validateParamsFastSMC()
+    return p
+
+
+@pytest.mark.parametrize("n_haps,n_sites,gap,min_m,two_pass", [(240, 3200, 1, 0.0, False), (400, 1920, 0, 0.05, True),
+                                                              (150, 6400, 2, 0.4, False)])
+def test_device_candidate_order_equals_literal_replay_on_dense_matches(asmc, tmp_path, monkeypatch, n_haps, n_sites, gap,
+                                                                       min_m, two_pass):
+    """Few founders: tens of thousands of short intervals, most of them never candidates but all of them nodes of the
+    reference's extend map; the map grows through many rehashes, buckets empty and refill.  The device ordering inside
+    fsmc_seed must hand the candidates over in the order of the LITERAL replay of the two boost maps (linked node lists,
+    CandidateOrder.hpp::replayReferenceOrder) over brute-force intervals."""
+    from fastsmc_b200 import synth
+    from test_host_layer import _brute_force_intervals
+    if two_pass:
+        monkeypatch.setenv("FSMC_ORDER_TWO_PASS", "1")  # creation sort as two stable passes (keys wider than 64 bits)
+    root = str(tmp_path / "dense")
+    synth.dataset(root, n_haps, n_sites, 3000 * n_sites, 1, 77 + n_haps, founders=6)
+    p = _synthetic_params(asmc, root, root + ".out", FASTSMC_EXAMPLE_DQ, gap=gap, min_m=min_m)
+    d = asmc.Data(p)
+    iv = _brute_force_intervals(np.array(d.hapBits), d.sites // 64, gap)
+    literal = np.array(asmc.pyASMC.replayReferenceOrder(iv, d, gap, min_m, fast=False))
+    want = iv[literal]
+    want = np.stack([want[:, 0], want[:, 1], want[:, 2] * 64, want[:, 3] * 64 + 63], axis=1)
+    f = asmc.FastSMC(p)
+    f.setKeepCandidates(True)
+    f.run()
+    got = f.getCandidates().astype(np.int64)
+    st = f.getSeedingStats().device
+    assert st.numIntervals == len(iv) and st.orderEpochs > 5 and len(want) > 100
+    assert len(got) == len(want) == st.numMatches
+    assert np.array_equal(got, want)
+
+
+def test_hashing_jobs_on_synthetic_data_equal_oracle(asmc, oracle_mod, tmp_path):
+    """cfg3-style hashing run on synthetic data, cut into jobs (jobs/jobInd windows, the last job with the remainder):
+    the decodeFromHashing call stream equals the oracle's (which walks real linked lists), and in exact mode every job's
+    .ibd.gz equals the oracle's line for line."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "syn")
+    synth.dataset(root, 1300, 6400, 64_000_000, 1, 4242)
+    for jobs, job_ind in ((4, 2), (4, 4), (1, 1)):
+        o = oracle_mod.Oracle(root, DQ_69, str(tmp_path / "o"), hashing=True, jobs=jobs, jobInd=job_ind, **REGRESSION_PARAMS)
+        want = o.seed().astype(np.int64)
+        p = _synthetic_params(asmc, root, str(tmp_path / f"gpu{jobs}_{job_ind}"), DQ_69, jobs=jobs, jobInd=job_ind,
+                              exactArithmetic=True)
+        f = asmc.FastSMC(p)
+        f.setKeepCandidates(True)
+        f.run()
+        got = f.getCandidates().astype(np.int64)
+        assert len(want) > 200 and np.array_equal(got, want)
+        ref_path = str(tmp_path / f"oracle{jobs}_{job_ind}.ibd.gz")
+        n = o.run(ref_path)
+        mine = _lines(f"{p.outFileRoot}.{job_ind}.{jobs}.FastSMC.ibd.gz")
+        assert len(mine) == n and mine == _lines(ref_path)
+
+
+def test_device_candidate_order_at_cfg3_density(asmc, oracle_mod, tmp_path):
+    """2 000 diploid samples x 50 000 SNPs at UKBB chr1 array density (cfg3's shape, a fifth of its samples): millions of
+    intervals, the extend map rehashes up to millions of buckets.  Candidate stream vs the oracle's seeding."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "cfg3s")
+    synth.dataset(root, 4000, 50_000, 240_000_000, 1, 20201117 + 3)
+    o = oracle_mod.Oracle(root, DQ_69, str(tmp_path / "o"), hashing=True, **REGRESSION_PARAMS)
+    want = o.seed().astype(np.int64)
+    p = _synthetic_params(asmc, root, str(tmp_path / "gpu"), DQ_69)
+    f = asmc.FastSMC(p)
+    f.setKeepCandidates(True)
+    f.run()
+    got = f.getCandidates().astype(np.int64)
+    st = f.getSeedingStats().device
+    assert st.numIntervals > 1_000_000 and st.orderEpochs > 15
+    assert len(got) == len(want) > 50_000
+    assert np.array_equal(got, want)

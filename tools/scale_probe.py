@@ -54,7 +54,9 @@ t0 = time.perf_counter()
 f.run()
 rep["run_s"] = time.perf_counter() - t0
 ss, st = f.getSeedingStats(), f.hmm().getRunStats()
-rep.update(seed_wall_s=ss.seedWallS, order_wall_s=ss.orderWallS, candidates=ss.candidates,
+rep.update(seed_wall_s=ss.seedWallS, order_wall_s=ss.orderWallS, submit_wall_s=ss.submitWallS, candidates=ss.candidates,
+           intervals=ss.device.numIntervals, order_device_ms=ss.device.orderMs, order_epochs=ss.device.orderEpochs,
+           rank_host_ms=ss.device.rankHostMs, max_live_nodes=ss.device.maxLiveNodes,
            seed_kernel_ms=ss.device.kernelMs, seed_launches=ss.device.kernelLaunches, pair_visits=ss.device.pairVisits,
            seed_starts=ss.device.numStarts, seed_matches=ss.device.numMatches, seed_bytes=ss.device.bytesRead,
            pairs_decoded=st.pairsDecoded, batches=st.batches, segments=st.segments, pair_sites=st.pairSites,
