@@ -65,6 +65,7 @@ class Stats(C.Structure):
         ("numSegments", C.c_int64), ("pairSites", C.c_double), ("kernelMs", C.c_float), ("totalMs", C.c_float),
         ("kernelLaunches", C.c_int32), ("statesKernel", C.c_int32), ("scratchBytes", C.c_int64),
         ("narrowKernel", C.c_int32), ("tileWarps", C.c_int32),
+        ("sparseKernel", C.c_int32), ("checkpointSites", C.c_int32), ("sparseItems", C.c_int64), ("checkpointBytes", C.c_int64),
     ]
 
 

@@ -2,6 +2,7 @@
 // Host side of the decode path: device buffers, model assembly, tile scheduling, launches.
 #include <algorithm>
 #include <atomic>
+#include <cub/device/device_radix_sort.cuh>
 #include <chrono>
 #include <cstdarg>
 #include <cstdint>
@@ -15,6 +16,7 @@
 
 #include "decode_kernels.cuh"
 #include "decode_fast.cuh"
+#include "decode_sparse.cuh"
 #include "seed_kernels.cuh"
 #include "seed_order.h"
 #include "host/SeedMapOrder.hpp"
@@ -125,6 +127,7 @@ struct fsmc_ctx {
   DevBuf<uint64_t> haps;
   long long numHaps = 0;
   DevBuf<float> scratch, accScratch;
+  DevBuf<float> ckptBeta;  // sparse age estimates: beta checkpoints of every tile of the current plan (decode_sparse.cuh)
   std::vector<float> hostPrior, hostExpTimes, hostColRatios;
   long long sites = 0;
   // seeding scratch (fsmc_seed)
@@ -177,6 +180,20 @@ struct fsmc_plan {
   bool narrow = false;
   int tileWarps = 1;
   int tilesPerBlock = 1;  // tiles in flight per CTA (= scratch slabs per CTA)
+  // sparse age estimates (decode_sparse.cuh)
+  bool sparse = false;
+  int ckptShift = 5;
+  long long ckptSlots = 0;
+  long long itemCapacity = 0;
+  long long itemsFound = 0;
+  DevBuf<long long> tileCkptBase;
+  DevBuf<float> alphaScratch, itemAlpha, itemSums;
+  DevBuf<fsmc::SparseItem> items;
+  DevBuf<uint32_t> itemKeys;  // [4][itemCapacity]: keys, sorted keys, indices, sorted indices
+  DevBuf<unsigned char> sortTemp;
+  size_t sortTempBytes = 0;
+  int refineBlocks = 0;
+  size_t refineSmem = 0;
 };
 
 namespace
@@ -225,6 +242,7 @@ struct FastChoice {
   int recordQuads = 0;
   int splitWarps = 0;       // > 0: decodeSplitKernel, one tile per CTA of this many warps (decode_split.cuh)
   size_t splitSmem = 0;
+  bool sparse = false;      // decodeNarrowKernel<SPARSE> + refineKernel (decode_sparse.cuh)
 };
 
 // FSMC_SPLIT=0 forces the one-warp-per-tile kernels, FSMC_SPLIT=1 the state-split kernels wherever one exists
@@ -236,7 +254,8 @@ int splitPreference()
 }
 // Without per-segment age estimates 8 warps (2 CTAs of 4) fit an SM; the accumulators of FSMC_SEG_AGE cost 8.6 KB of
 // shared memory per warp, which leaves room for 7 warps (1 CTA).
-FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
+// preferSparse: the request's scan windows are long (all-pairs decoding): IBD runs cover a small part of them
+FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bool preferSparse = false)
 {
   const int S = m.S;
   // full posteriors and their sums are produced by decodeTilesKernel only
@@ -261,6 +280,29 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags)
       fc.splitSmem = sc.smemBytes;
       return fc;
     }
+  }
+  // all-state age estimates of sparse IBD runs: narrow sweeps + checkpoints, full posteriors only inside the runs
+  const bool sparse = preferSparse && S == 69 && acc && m.ageThreshold > m.stateThreshold &&
+                      !(flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP | FSMC_WIDE_KERNEL)) && m.stateThreshold + 1 <= 4 * fsmc::kNarrowMaxQuads;
+  if (sparse) {
+    const int rq = (m.stateThreshold + 1 + 3) / 4;
+    FastKernelFn fn = rq == 1   ? fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 1>
+                      : rq == 2 ? fsmc::decodeNarrowKernel<69, 2, 4, kFastDepth, 128, 2, 1>
+                      : rq == 3 ? fsmc::decodeNarrowKernel<69, 3, 2, kFastDepth, 128, 2, 1>
+                                : fsmc::decodeNarrowKernel<69, 4, 2, kFastDepth, 128, 2, 1>;
+    if (const char* e = std::getenv("FSMC_SPARSE_VARIANT")) {  // timing experiments (results are wrong)
+      const int v = std::atoi(e);
+      if (rq == 1 && v == 3) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 3>;
+      if (rq == 1 && v == 5) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 5>;
+      if (rq == 1 && v == 7) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 7>;
+      if (rq == 1 && v == 9) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 9>;
+      if (rq == 1 && v == 17) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 17>;
+      if (rq == 1 && v == 33) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 33>;
+      if (rq == 1 && v == 57) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 57>;
+    }
+    FastChoice fc{fn, 72, 128, false, true, rq};
+    fc.sparse = true;
+    return fc;
   }
   if (S == 69 && narrow) {
     // 2 CTAs x 4 warps per SM at 255 registers: measured 12.2e9 pair-sites/s vs 10.1e9 at 3 CTAs / 168 registers (spills)
@@ -523,7 +565,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   }
   const DeviceModel& m = ctx->model;
   long long maxLen = 0;
-  double pairSites = 0.0;
+  double pairSites = 0.0, scanSites = 0.0;
   for (long long t = 0; t < T; ++t) {
     const int n = req->tilePairs[t], f = req->tileFrom[t], e = req->tileTo[t];
     if (n < 1 || n > FSMC_TILE || f < 0 || e > m.L || e <= f) {
@@ -541,6 +583,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     }
     maxLen = std::max<long long>(maxLen, e - f);
     pairSites += static_cast<double>(n) * (e - f);
+    scanSites += seg ? static_cast<double>(req->tileScanTo[t] - req->tileScanFrom[t]) : 0.0;
   }
   if (siteOut && req->siteStride < maxLen) {
     return fail(FSMC_E_INVALID, "fsmc_plan_create: siteStride=%lld < longest window %lld",
@@ -627,8 +670,16 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   // ---- launch geometry --------------------------------------------------------------------------
   const KernelChoice kc = chooseKernel(m.S, flags);
-  const FastChoice fc = chooseFastKernel(m, flags);
+  // Sparse age estimates pay off when IBD runs cover a small part of the scan windows: whole-chromosome windows
+  // (all-pairs decoding, hashing off).  The windows of hashing candidates lie mostly inside runs: dense kernel.
+  // FSMC_SPARSE=0/1 overrides the window-length rule (development / tests).
+  bool preferSparse = T > 0 && scanSites / static_cast<double>(T) >= 2000.0;
+  if (const char* e = std::getenv("FSMC_SPARSE")) {
+    preferSparse = std::atoi(e) != 0;
+  }
+  const FastChoice fc = chooseFastKernel(m, flags, preferSparse);
   plan->fast = fc.fn != nullptr;
+  plan->sparse = fc.sparse;
   plan->statesKernel = plan->fast ? m.S : kc.statesKernel;
   plan->narrow = fc.narrow;
   plan->tileWarps = fc.splitWarps > 0 ? fc.splitWarps : 1;
@@ -687,10 +738,87 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   plan->blocks = static_cast<int>(blocks);
   plan->tilesPerBlock = warpsPerBlock;
+
+  if (plan->sparse) {
+    // ---- checkpoints, items and the refine pass (decode_sparse.cuh) -------------------------------------------------
+    const size_t vecFloats = static_cast<size_t>(fc.Spad) * 32;
+    size_t freeB = 0, totalB = 0;
+    FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
+    const double budget = 0.45 * static_cast<double>(freeB + ctx->ckptBeta.n * sizeof(float));
+    // blocks of 128 sites (measured on cfg2: 401 / 378 / 364 / 359 ms per step with blocks of 32 / 64 / 128 / 256 sites:
+    // every block boundary inside an IBD run costs the warp an item, and every block a checkpoint); coarser when the
+    // checkpoints of the whole request would not fit
+    int shift = 7;
+    if (const char* e = std::getenv("FSMC_CKPT_SHIFT")) {
+      shift = std::max(2, std::min(10, std::atoi(e)));
+    }
+    std::vector<long long> base(static_cast<size_t>(T) + 1, 0);
+    for (;; ++shift) {
+      long long slots = 0;
+      for (long long t = 0; t < T; ++t) {
+        base[t] = slots;
+        slots += ((req->tileTo[t] - 1) >> shift) - (req->tileFrom[t] >> shift) + 1;
+      }
+      base[T] = slots;
+      if (static_cast<double>(slots) * vecFloats * sizeof(float) <= budget || shift >= 12) {
+        break;
+      }
+    }
+    plan->ckptShift = shift;
+    plan->ckptSlots = base[T];
+    FSMC_CUDA(ctx->ckptBeta.ensure(static_cast<size_t>(plan->ckptSlots) * vecFloats));
+    FSMC_CUDA(plan->tileCkptBase.ensure(static_cast<size_t>(T) + 1));
+    FSMC_CUDA(cudaMemcpyAsync(plan->tileCkptBase.p, base.data(), (static_cast<size_t>(T) + 1) * sizeof(long long),
+                              cudaMemcpyHostToDevice, st));
+    FSMC_CUDA(cudaStreamSynchronize(st));  // `base` goes out of scope
+    FSMC_CUDA(plan->alphaScratch.ensure(static_cast<size_t>(blocks) * warpsPerBlock * vecFloats));
+    FSMC_CUDA(plan->counters.ensure(4));
+    // items: one per (run, block).  Start from one item per 512 pair-sites (all-pairs data sets have one per ~1500);
+    // fsmc_plan_collect re-runs the request with a larger buffer if that was not enough.
+    if (plan->itemCapacity == 0) {
+      plan->itemCapacity = std::max<long long>(1 << 16, static_cast<long long>(pairSites / 512.0));
+    }
+    if (const char* e = std::getenv("FSMC_ITEM_CAPACITY")) {  // tests: force the overflow / re-run path
+      plan->itemCapacity = std::max<long long>(1, std::atoll(e));
+    }
+    plan->itemCapacity = std::min<long long>(plan->itemCapacity, 0x7ffffff0ll);
+    // refine pass geometry
+    auto refineFn = fsmc::refineKernel<69, fsmc::kRefineDepth, kFastRescale, 128, 2>;
+    plan->refineSmem = 4 * (fsmc::kRefineDepth * (vecFloats * 4 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4)) +
+                       4 * 2 * fsmc::kRefineDepth * sizeof(uint64_t);
+    FSMC_CUDA(cudaFuncSetAttribute(refineFn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->refineSmem)));
+    int perSm = 0;
+    FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, refineFn, 128, plan->refineSmem));
+    if (perSm < 1) {
+      return fail(FSMC_E_CUDA, "fsmc_plan_create: refine kernel does not fit on an SM (smem=%zu)", plan->refineSmem);
+    }
+    plan->refineBlocks = ctx->prop.multiProcessorCount * perSm;
+    const size_t refineScratch = static_cast<size_t>(plan->refineBlocks) * 4 * (size_t{1} << shift) * vecFloats;
+    FSMC_CUDA(ctx->scratch.ensure(std::max<size_t>(refineScratch, static_cast<size_t>(blocks) * static_cast<size_t>(warpsPerBlock) * static_cast<size_t>(plan->scratchPerWarp))));
+  }
   guard.keep = true;
   *out = plan;
   return FSMC_OK;
 }
+
+namespace
+{
+// item buffers of a sparse plan, (re)sized to plan->itemCapacity
+int allocateItems(fsmc_plan* plan, const int Spad)
+{
+  const size_t cap = static_cast<size_t>(plan->itemCapacity);
+  FSMC_CUDA(plan->items.ensure(cap));
+  FSMC_CUDA(plan->itemAlpha.ensure(cap * Spad));
+  FSMC_CUDA(plan->itemSums.ensure(cap * Spad));
+  FSMC_CUDA(plan->itemKeys.ensure(4 * cap));
+  size_t bytes = 0;
+  uint32_t* k = plan->itemKeys.p;
+  FSMC_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, bytes, k, k, k, k, static_cast<int>(cap)));
+  FSMC_CUDA(plan->sortTemp.ensure(bytes));
+  plan->sortTempBytes = bytes;
+  return FSMC_OK;
+}
+}  // namespace
 
 int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
 {
@@ -703,8 +831,25 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
   FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
   plan->launches = 0;
   if (plan->numTiles > 0) {
-    FSMC_CUDA(cudaMemsetAsync(plan->counters.p, 0, 2 * sizeof(unsigned long long), st));
+    FSMC_CUDA(cudaMemsetAsync(plan->counters.p, 0, (plan->sparse ? 4 : 2) * sizeof(unsigned long long), st));
     DecodeArgs a{};
+    if (plan->sparse) {
+      const int rc = allocateItems(plan, m.Spad);
+      if (rc != FSMC_OK) {
+        return rc;
+      }
+      a.ckptShift = plan->ckptShift;
+      a.tileCkptBase = plan->tileCkptBase.p;
+      a.ckptBeta = ctx->ckptBeta.p;
+      a.alphaScratch = plan->alphaScratch.p;
+      a.items = plan->items.p;
+      a.itemAlpha = plan->itemAlpha.p;
+      a.itemSums = plan->itemSums.p;
+      a.itemCount = plan->counters.p + 2;
+      a.itemCapacity = plan->itemCapacity;
+      a.itemOrder = plan->itemKeys.p + 3 * static_cast<size_t>(plan->itemCapacity);
+      a.refineCounter = plan->counters.p + 3;
+    }
     a.hapA = plan->hapA.p;
     a.hapB = plan->hapB.p;
     a.tilePairs = plan->tilePairs.p;
@@ -737,14 +882,32 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
       std::copy(ctx->hostColRatios.begin(), ctx->hostColRatios.end(), fm.colRatios);
       std::copy(ctx->hostExpTimes.begin(), ctx->hostExpTimes.end(), fm.expTimes);
       std::copy(ctx->hostPrior.begin(), ctx->hostPrior.end(), fm.prior);
-      const FastChoice fc = chooseFastKernel(m, plan->flags);
+      const FastChoice fc = chooseFastKernel(m, plan->flags, plan->sparse);
       fc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(fm, a);
+      if (plan->sparse) {
+        // items by block, full posteriors inside the items, age estimates of the segments
+        const long long cap = plan->itemCapacity;
+        uint32_t* keys = plan->itemKeys.p;
+        uint32_t* keysOut = keys + cap;
+        uint32_t* index = keys + 2 * cap;
+        uint32_t* indexOut = keys + 3 * cap;
+        const int kb = static_cast<int>(std::min<long long>((cap + 255) / 256, ctx->prop.multiProcessorCount * 8ll));
+        fsmc::itemKeysKernel<<<kb, 256, 0, st>>>(a.items, a.itemCount, cap, keys, index);
+        size_t bytes = plan->sortTempBytes;
+        FSMC_CUDA(cub::DeviceRadixSort::SortPairs(plan->sortTemp.p, bytes, keys, keysOut, index, indexOut, static_cast<int>(cap), 0, 32, st));
+        DecodeArgs r = a;
+        r.scratchPerWarp = (1ll << plan->ckptShift) * m.Spad * 32;
+        fsmc::refineKernel<69, fsmc::kRefineDepth, kFastRescale, 128, 2><<<plan->refineBlocks, 128, plan->refineSmem, st>>>(fm, r);
+        fsmc::finalizeSegmentsKernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, st>>>(m, a.segments, a.segmentCount, a.segmentCapacity,
+                                                                                          a.items, a.itemSums, a.itemCount, cap);
+        plan->launches += 4;
+      }
     } else {
       const KernelChoice kc = chooseKernel(m.S, plan->flags);
       kc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(m, a);
     }
     FSMC_CUDA(cudaGetLastError());
-    plan->launches = 1;
+    plan->launches += 1;
   }
   FSMC_CUDA(cudaEventRecord(ctx->ev[2], st));
   plan->launched = true;
@@ -762,11 +925,27 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
   FSMC_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const unsigned flags = plan->flags;
-  unsigned long long counters[2] = {0, 0};
-  if (plan->numTiles > 0) {
-    FSMC_CUDA(cudaMemcpyAsync(counters, plan->counters.p, sizeof counters, cudaMemcpyDeviceToHost, st));
+  unsigned long long counters[4] = {0, 0, 0, 0};
+  for (;;) {
+    if (plan->numTiles > 0) {
+      FSMC_CUDA(cudaMemcpyAsync(counters, plan->counters.p, (plan->sparse ? 4 : 2) * sizeof(unsigned long long),
+                                cudaMemcpyDeviceToHost, st));
+    }
+    FSMC_CUDA(cudaStreamSynchronize(st));
+    plan->itemsFound = static_cast<long long>(counters[2]);
+    if (!plan->sparse || plan->itemsFound <= plan->itemCapacity) {
+      break;
+    }
+    // more run pieces than item slots: run the request again with enough of them (the launch re-allocates)
+    if (plan->itemsFound >= 0x7ffffff0ll) {
+      return fail(FSMC_E_NOMEM, "fsmc_plan_collect: %lld run pieces in one request; decode fewer tiles per call", plan->itemsFound);
+    }
+    plan->itemCapacity = std::min<long long>(plan->itemsFound + plan->itemsFound / 8 + 1024, 0x7ffffff0ll);
+    const int rc = fsmc_plan_launch(ctx, plan);
+    if (rc != FSMC_OK) {
+      return rc;
+    }
   }
-  FSMC_CUDA(cudaStreamSynchronize(st));
   const long long found = static_cast<long long>(counters[0]);
   const long long stored = std::min<long long>(found, plan->segmentCapacity);
   int rc = FSMC_OK;
@@ -856,6 +1035,10 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
     stats->narrowKernel = plan->narrow ? 1 : 0;
     stats->tileWarps = plan->tileWarps;
     stats->scratchBytes = static_cast<int64_t>(plan->scratchPerWarp) * sizeof(float) * plan->blocks * plan->tilesPerBlock;
+    stats->sparseKernel = plan->sparse ? 1 : 0;
+    stats->sparseItems = plan->sparse ? plan->itemsFound : 0;
+    stats->checkpointBytes = plan->sparse ? plan->ckptSlots * static_cast<int64_t>(ctx->model.Spad) * 32 * 4 : 0;
+    stats->checkpointSites = plan->sparse ? (1 << plan->ckptShift) : 0;
   }
   plan->launched = false;
   return rc;

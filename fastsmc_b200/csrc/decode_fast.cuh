@@ -277,6 +277,38 @@ __device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[
   return run;
 }
 
+// One item per lane with `pred` (decode_sparse.cuh): slots from one atomic per warp, the descriptor, and alpha at the block's
+// first site (copied from the warp's scratch, column `lane`).  Returns the lane's new chain head.  Out of line on purpose:
+// it runs at a few percent of the sites, and inlined into the unrolled site loop it slowed every site down (the loop no
+// longer streamed from the instruction cache: 413 ms instead of 329 ms per cfg2 step).
+static __device__ __noinline__ int emitSparseItems(SparseItem* items, float* itemAlpha, unsigned long long* itemCount,
+                                            const long long capacity, const bool pred, const uint32_t pair, const int block,
+                                            const int first, const int last, int chain, const float4* alphaStart,
+                                            const int lane, const int SQ)
+{
+  const unsigned mask = __ballot_sync(kFull, pred);
+  if (!mask) {
+    return chain;
+  }
+  unsigned long long base = 0;
+  if (lane == 0) {
+    base = atomicAdd(itemCount, static_cast<unsigned long long>(__popc(mask)));
+  }
+  base = __shfl_sync(kFull, base, 0);
+  if (pred) {
+    const long long slot = static_cast<long long>(base) + __popc(mask & ((1u << lane) - 1u));
+    if (slot < capacity) {
+      items[slot] = SparseItem{pair, block, first, last, chain};
+      float4* dst = reinterpret_cast<float4*>(itemAlpha + static_cast<size_t>(slot) * SQ * 4);
+      for (int q = 0; q < SQ; ++q) {
+        dst[q] = alphaStart[q * 32 + lane];
+      }
+    }
+    chain = static_cast<int>(slot);
+  }
+  return chain;
+}
+
 // -------------------------------------------------------------------------------------------------------------------
 // decodeNarrowKernel: the same sweeps WITHOUT the beta round trip, for requests that only look at the states below the
 // IBD time threshold (segment calling, per-site IBD probability, and age estimates conditioned on TMRCA < threshold,
@@ -307,9 +339,19 @@ template <int S_T, int RQ, int G> struct NarrowSlot {
 // of consecutive positions in the slab), so the per-site cost outside the recurrences is the genotype class lookup,
 // the record (RQ shared-memory accesses) and the segment caller.  Rescaling happens at the last step of every full
 // group, i.e. every G-th site.
-template <int S_T, int RQ, int G, int DEPTH, int THREADS, int MIN_BLOCKS>
+//
+// SPARSE (decode_sparse.cuh): age estimates over ALL states without a beta round trip.  The kernel additionally leaves
+// a full beta vector at the last site of every block of 2^ckptShift sites (checkpoints, 8*S/2^ckptShift bytes per
+// pair-site), keeps alpha of the current block's first site in a per-warp scratch that stays in L2, and records every
+// piece of an IBD run (one item per run and block) together with that alpha.  The refine pass recomputes the full
+// posterior only inside those pieces.
+template <int S_T, int RQ, int G, int DEPTH, int THREADS, int MIN_BLOCKS, int SPARSE_V = 0>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const FastModel fm, const DecodeArgs args)
 {
+  constexpr bool SPARSE = (SPARSE_V & 1) != 0;
+  constexpr bool kSkipFwd = (SPARSE_V & 2) != 0, kSkipBwd = (SPARSE_V & 4) != 0;  // timing experiments only
+  constexpr int kGroupUnroll = SPARSE ? 1 : G / 2;
+  constexpr bool kSkipAlpha = (SPARSE_V & 8) != 0, kSkipBoundaryItems = (SPARSE_V & 16) != 0, kSkipRunItems = (SPARSE_V & 32) != 0;
   constexpr int S = S_T;
   constexpr int SQ = (S + 3) / 4;
   constexpr int Spad = SQ * 4;
@@ -345,10 +387,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
 
   const unsigned flags = args.flags;
   const bool wantSeg = flags & FSMC_CALL_SEGMENTS;
-  const bool wantAge = (flags & FSMC_SEG_AGE) && wantSeg;
+  const bool wantAge = !SPARSE && (flags & FSMC_SEG_AGE) && wantSeg;  // SPARSE: the refine pass computes the age estimates
   const int sT = m.stateThreshold;  // <= NR by the host's kernel choice
   const long long warpGlobal = static_cast<long long>(blockIdx.x) * kWarps + warp;
   float* slab = args.scratch + warpGlobal * args.scratchPerWarp;
+  constexpr size_t kVecFloats = static_cast<size_t>(SQ) * 32 * 4;  // one state vector of the warp, [quad][lane][4]
+  const int ckShift = SPARSE ? args.ckptShift : 0;
+  const int ckMask = (1 << ckShift) - 1;
+  float4* alphaStart = SPARSE ? reinterpret_cast<float4*>(args.alphaScratch + warpGlobal * kVecFloats) : nullptr;
 
   for (;;) {
     unsigned long long t = 0;
@@ -372,6 +418,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
     bits.a = m.haps + static_cast<size_t>(args.hapA[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
     bits.b = m.haps + static_cast<size_t>(args.hapB[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
     const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowFloats;
+    // SPARSE: checkpoint slot of block b of this tile = ckptSlot0 + b
+    const long long ckptSlot0 = SPARSE ? args.tileCkptBase[tile] - (from >> ckShift) : 0;
+    // full state vector of the warp -> [quad][lane][4] in global memory (coalesced 512-byte rows)
+    auto storeVector = [&](const float (&v)[S], float4* dst) {
+#pragma unroll
+      for (int q = 0; q < SQ; ++q) {
+        dst[q * 32 + lane] = make_float4(v[4 * q], 4 * q + 1 < S ? v[4 * q + 1] : 0.f, 4 * q + 2 < S ? v[4 * q + 2] : 0.f,
+                                         4 * q + 3 < S ? v[4 * q + 3] : 0.f);
+      }
+    };
+    auto storeCheckpoint = [&](const float (&v)[S], const int site) {
+      storeVector(v, reinterpret_cast<float4*>(args.ckptBeta + static_cast<size_t>(ckptSlot0 + (site >> ckShift)) * kVecFloats));
+    };
 
     float a[S], c[S];
     float acc[NR];
@@ -414,6 +473,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
       for (int k = 0; k < S; ++k) {
         a[k] = 1.f;
       }
+      if constexpr (SPARSE) {
+        storeCheckpoint(a, from + len - 1);  // the window's last block ends at its last site (beta = ones)
+      }
       if (nGroups == 0) {
         // single-site window: only the all-ones record
         stageRecord(a, recArea(0), 1.0f);
@@ -449,8 +511,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
             scaleStates<S>(y, 1.0f / divisor);
           }
           stageRecord(y, stage + static_cast<size_t>(n - 1 - i) * RQ * 32, divisor);
+          if constexpr (SPARSE && !kSkipBwd) {
+            if (((from + p) & ckMask) == ckMask) {  // last site of a block
+              storeCheckpoint(y, from + p);
+            }
+          }
         };
-#pragma unroll
+        // SPARSE: not unrolled, one copy of each step direction.  Unrolled over the group the two sweeps are ~7 000
+        // instructions (110 KB) of straight-line code and the kernel sits at the capacity of the instruction cache: with
+        // the sparse bookkeeping added, "no instruction" became its first stall (profiles/r2_v4_decodeNarrowSparse_ncu_full.txt).
+#pragma unroll(kGroupUnroll)
         for (int i = 0; i < G; i += 2) {
           if (i < n) {
             step(i, a, c, false);
@@ -503,10 +573,35 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
       }
       CallerState cs;
       float Z = 1.f, bPrev = 1.f;
+      // SPARSE: the open piece of the lane's current run (sites pieceStart.. in the current block) and the chain of the
+      // run's earlier pieces
+      bool runOpen = false;
+      int pieceStart = 0, chain = -1;
+      auto emitItems = [&](const bool pred, const int block, const int first, const int last) {
+        chain = emitSparseItems(args.items, args.itemAlpha, args.itemCount, args.itemCapacity, pred, pair, block, first, last, chain,
+                                alphaStart, lane, SQ);
+      };
 
       // consumers of window position p; v = alpha^(p); rec = this position's record (parking area once drained)
       auto consume = [&](const int p, const float (&v)[S], float4* rec) {
         const int site = from + p;
+        if constexpr (SPARSE && !kSkipFwd) {
+          const bool boundary = (site & ckMask) == 0 && p > 0;
+          if (boundary) {
+            // a run that continues into this block leaves the piece of the block that just ended
+            if constexpr (!kSkipBoundaryItems) {
+              if (__any_sync(kFull, runOpen)) {
+                emitItems(runOpen, (site - 1) >> ckShift, pieceStart, site - 1);
+              }
+            }
+            pieceStart = site;
+          }
+          if constexpr (!kSkipAlpha) {
+            if (boundary || p == 0) {
+              storeVector(v, alphaStart);  // same lanes read it back: no synchronisation needed
+            }
+          }
+        }
         float q[4 * RQ];  // alpha^[k] beta^[k] for k < sT (0 above); q[NR] = b_p
 #pragma unroll
         for (int qq = 0; qq < RQ; ++qq) {
@@ -539,7 +634,35 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
           const bool closing = now >= 0 && site == scanTo - 1;
           const float rr = now >= 0 ? r : 0.f;
           const float keep = changed ? 0.f : 1.f;
-          if (__any_sync(kFull, ending || closing)) {
+          if constexpr (SPARSE && !kSkipFwd) {
+            if (__any_sync(kFull, ending || closing)) {
+              // the run's last piece, then the record; the refine pass fills in the age estimates from the chain
+              if constexpr (!kSkipRunItems) {
+                emitItems(ending && runOpen && pieceStart <= site - 1, (site - 1) >> ckShift, pieceStart, site - 1);
+              }
+              if (ending) {
+                emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, nullptr, false, chain);
+                chain = -1;
+                runOpen = false;
+              }
+              if (now >= 0 && changed) {
+                runOpen = true;
+                pieceStart = site;
+              }
+              if constexpr (!kSkipRunItems) {
+                emitItems(closing, site >> ckShift, pieceStart, site);
+              }
+              if (closing) {
+                emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, nullptr,
+                                   false, chain);
+                chain = -1;
+                runOpen = false;
+              }
+            } else if (now >= 0 && changed) {
+              runOpen = true;
+              pieceStart = site;
+            }
+          } else if (__any_sync(kFull, ending || closing)) {
             // rare: a run ends at site-1 and/or the scan window closes on a live run
             float* park = reinterpret_cast<float*>(rec) + lane;  // drained record: [k][32], k < NR
             __syncwarp();
@@ -598,38 +721,35 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
           Z *= bPrev * sc;  // Z_p = Z_{p-1} * b_{p-1} / a_p
           consume(p, y, recs + static_cast<size_t>(i) * RQ * 32);
         };
-        if (g == 0) {
-          // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
-          const int cls = bits.cls(from);
-          const float4* E = reinterpret_cast<const float4*>(coef + cls * Spad);
-          float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
+#pragma unroll(kGroupUnroll)
+        for (int i = 0; i < G; i += 2) {  // SPARSE: one copy of each step direction (instruction-cache footprint, see sweep 1)
+          if (i == 0 && g == 0) {
+            // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
+            const int cls = bits.cls(from);
+            const float4* E = reinterpret_cast<const float4*>(coef + cls * Spad);
+            float z0 = 0.f, z1 = 0.f, z2 = 0.f, z3 = 0.f;
 #pragma unroll
-          for (int q = 0; q < SQ; ++q) {
-            const float4 e4 = E[q];
+            for (int q = 0; q < SQ; ++q) {
+              const float4 e4 = E[q];
 #pragma unroll
-            for (int i = 0; i < 4; ++i) {
-              const int k = 4 * q + i;
-              if (k < S) {
-                a[k] = fm.prior[k] * f4(e4, i);
+              for (int j = 0; j < 4; ++j) {
+                const int k = 4 * q + j;
+                if (k < S) {
+                  a[k] = fm.prior[k] * f4(e4, j);
+                }
               }
+              z0 = fmaf(a[4 * q], c[4 * q], z0);
+              if (4 * q + 1 < S) z1 = fmaf(a[4 * q + 1], c[4 * q + 1], z1);
+              if (4 * q + 2 < S) z2 = fmaf(a[4 * q + 2], c[4 * q + 2], z2);
+              if (4 * q + 3 < S) z3 = fmaf(a[4 * q + 3], c[4 * q + 3], z3);
             }
-            z0 = fmaf(a[4 * q], c[4 * q], z0);
-            if (4 * q + 1 < S) z1 = fmaf(a[4 * q + 1], c[4 * q + 1], z1);
-            if (4 * q + 2 < S) z2 = fmaf(a[4 * q + 2], c[4 * q + 2], z2);
-            if (4 * q + 3 < S) z3 = fmaf(a[4 * q + 3], c[4 * q + 3], z3);
+            Z = (z0 + z1) + (z2 + z3);
+            consume(0, a, recs);
+          } else if (i < n) {
+            step(i, c, a, false);
           }
-          Z = (z0 + z1) + (z2 + z3);
-          consume(0, a, recs);
-        } else {
-          step(0, c, a, false);
-        }
-#pragma unroll
-        for (int i = 1; i < G; i += 2) {
-          if (i < n) {
-            step(i, a, c, i == G - 1);
-          }
-          if (i + 1 < G && i + 1 < n) {
-            step(i + 1, c, a, false);
+          if (i + 1 < n) {
+            step(i + 1, a, c, i + 1 == G - 1);
           }
         }
         __syncwarp();  // the slot is drained (its records double as the parking area above)

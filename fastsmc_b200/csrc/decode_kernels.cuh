@@ -46,6 +46,15 @@ struct DeviceModel {
   long long wordsPerHap;
 };
 
+// One piece of an IBD run inside one checkpoint block: sites [first, last] of pair `pair`.  The pieces of a run are
+// chained through `prev` (the segment record points at the last one).
+struct SparseItem {
+  uint32_t pair;
+  int32_t block;
+  int32_t first, last;
+  int32_t prev;
+};
+
 struct DecodeArgs {
   const uint32_t* hapA;
   const uint32_t* hapB;
@@ -70,6 +79,18 @@ struct DecodeArgs {
   long long scratchPerWarp;    // floats per warp slab
   float* accScratch;           // fast kernel: per-warp [S][32] per-state segment sums
   unsigned long long* tileCounter;
+  // ---- sparse age estimates (decode_sparse.cuh): all-state per-segment sums without the beta round trip ------------
+  int ckptShift;                    // checkpoint block = 2^ckptShift sites, aligned to absolute site numbers
+  const long long* tileCkptBase;    // [numTiles] first checkpoint slot of each tile
+  float* ckptBeta;                  // [slot][Spad/4][32][4] beta at the last site of every block of every tile
+  float* alphaScratch;              // [resident warp][Spad/4][32][4] alpha at the first site of the block being swept
+  SparseItem* items;                // pieces of IBD runs, one per (run, block)
+  float* itemAlpha;                 // [item][Spad] alpha at the first site of the item's block (or of the window)
+  float* itemSums;                  // [item][Spad] per-state posterior sums over the item's sites (refine pass)
+  unsigned long long* itemCount;
+  long long itemCapacity;
+  const uint32_t* itemOrder;        // items sorted by block (refine pass)
+  unsigned long long* refineCounter;
 };
 
 // ---- arithmetic: EXACT = separate IEEE multiply and add (never contracted), else FMA ------------
@@ -270,7 +291,8 @@ __device__ __forceinline__ void sweepBackward(const DeviceModel& m, PairBits& bi
 template <bool EXACT>
 __device__ __noinline__ void emitSegment(const DeviceModel& m, const DecodeArgs& a, const uint32_t pair, const int start,
                                          const int end, const float prob, const int level,
-                                         const float* acc /* smem + lane, stride 32 */, const bool age)
+                                         const float* acc /* smem + lane, stride 32 */, const bool age,
+                                         const int lastItem = -1 /* sparse age estimates: chain of the run's items */)
 {
   fsmc_segment s;
   s.pair = pair;
@@ -280,7 +302,7 @@ __device__ __noinline__ void emitSegment(const DeviceModel& m, const DecodeArgs&
   s.level = level;
   s.postMean = 0.f;
   s.mapTime = 0.f;
-  s.mapState = -1;
+  s.mapState = lastItem;  // replaced by finalizeSegmentsKernel (decode_sparse.cuh) when >= 0
   if (age) {
     const int n = m.ageThreshold;
     float tot = 0.f;

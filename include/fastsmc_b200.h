@@ -165,6 +165,12 @@ typedef struct fsmc_decode_stats {
   int64_t scratchBytes; /* backward-sweep scratch in HBM                                          */
   int32_t narrowKernel; /* 1 if the kernel without the beta round trip ran (states < threshold only) */
   int32_t tileWarps;    /* warps that shared a tile: 1, or 2 / 4 for the state-split kernels                */
+  /* all-state age estimates without the beta round trip (csrc/decode_sparse.cuh): narrow sweeps + checkpoints, then
+   * full posteriors only inside the IBD runs                                                                        */
+  int32_t sparseKernel;     /* 1 if that path ran                                                  */
+  int32_t checkpointSites;  /* sites per checkpoint block                                           */
+  int64_t sparseItems;      /* run pieces (one per run and block) refined                           */
+  int64_t checkpointBytes;  /* beta checkpoints in HBM                                              */
 } fsmc_decode_stats;
 
 int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats* stats);

@@ -254,8 +254,11 @@ def test_fast_kernel_segments_69_states(synthetic69, split):
     want = {(int(i[0]) * 32 + int(i[1]), int(i[4]), int(i[5])): f for i, f in zip(ints, floats)}
     got = {(int(s["pair"]), int(s["posStart"]), int(s["posEnd"])): s for s in seg}
     common = set(want) & set(got)
-    # identical segment lists up to threshold ties
-    assert len(common) >= 0.999 * max(len(want), len(got)) and abs(len(seg) - n) <= 0.001 * n + 2
+    # identical segment lists, except where the posterior is within tolerance of a threshold (checked site by site
+    # against the oracle's per-site IBD probability for every pair whose lists differ)
+    assert len(common) >= 0.995 * max(len(want), len(got)) and abs(len(seg) - n) <= 0.005 * n + 2
+    from conftest import check_segments_up_to_threshold_ties
+    check_segments_up_to_threshold_ties(o, seg, want.keys(), lambda p: (a[p], b[p]), REL_TOL)
     w = np.array([want[k] for k in sorted(common)])
     g = np.array([[got[k]["prob"], got[k]["postMean"], got[k]["mapTime"]] for k in sorted(common)])
     np.testing.assert_allclose(g[:, 0], w[:, 0], rtol=REL_TOL)
@@ -370,3 +373,93 @@ def test_one_warp_kernels_still_selectable_159(example):
     for r in (r1, r4):
         np.testing.assert_allclose(r.site_mean[tiles["rows"], :500], mean, rtol=REL_TOL)
         np.testing.assert_allclose(r.site_ibd[tiles["rows"], :500], ibd, rtol=REL_TOL, atol=1e-12)
+
+
+# ---- all-state age estimates without the beta round trip (decode_sparse.cuh) -------------------------------------------
+
+
+def _all_pairs(H):
+    a, b = [], []
+    for i in range(H // 2):
+        for j in range(i):
+            for ih in (0, 1):
+                for jh in (0, 1):
+                    a.append(2 * j + jh)
+                    b.append(2 * i + ih)
+        a.append(2 * i)
+        b.append(2 * i + 1)
+    return np.array(a), np.array(b)
+
+
+def _seg_key(s):
+    return (int(s["pair"]), int(s["posStart"]), int(s["posEnd"]))
+
+
+def test_sparse_age_estimates_match_oracle_and_dense_kernel(synthetic69, monkeypatch):
+    """noConditionalAgeEstimates on whole-chromosome windows: narrow sweeps + checkpoints + refinement inside the IBD runs
+    (sparseKernel) vs the oracle (1e-4) and vs the kernel that streams every beta row through HBM (same segments)."""
+    from conftest import check_segments_up_to_threshold_ties
+    from fastsmc_b200 import _native as N
+    o, ctx = synthetic69
+    n = o.run("/tmp/fsmc_test69_oracle.ibd.gz")
+    ints, floats = o.segments()
+    a, b = _all_pairs(o.num_haps)
+    tiles = ctx.make_tiles(a, b, sites=o.sites)
+    flags = N.CALL_SEGMENTS | N.SEG_AGE
+    want = {(int(i[0]) * 32 + int(i[1]), int(i[4]), int(i[5])): (f, int(i[6])) for i, f in zip(ints, floats)}
+    dense = ctx.decode(tiles, flags | N.WIDE_KERNEL, segment_capacity=1 << 20)
+    assert dense.stats.sparseKernel == 0 and dense.stats.narrowKernel == 0
+    gd = {_seg_key(s): s for s in dense.segments}
+    results = {}
+    for label, env in (("default", {}), ("blocks of 8", {"FSMC_CKPT_SHIFT": "3"}), ("blocks of 32", {"FSMC_CKPT_SHIFT": "5"}),
+                       ("item overflow", {"FSMC_ITEM_CAPACITY": "1000"})):
+        for k, v in env.items():
+            monkeypatch.setenv(k, v)
+        r = ctx.decode(tiles, flags, segment_capacity=1 << 20)
+        for k in env:
+            monkeypatch.delenv(k)
+        st = r.stats
+        assert st.sparseKernel == 1 and st.narrowKernel == 1 and st.sparseItems > len(r.segments) > 1000, label
+        assert st.checkpointSites == {"blocks of 8": 8, "blocks of 32": 32}.get(label, 128)
+        got = {_seg_key(s): s for s in r.segments}
+        results[label] = got
+        common = sorted(set(want) & set(got))
+        assert len(common) >= 0.995 * max(len(want), len(got)) and abs(len(got) - n) <= 0.005 * n + 2, label
+        if label == "default":
+            check_segments_up_to_threshold_ties(o, r.segments, want.keys(), lambda p: (a[p], b[p]), REL_TOL)
+        g = np.array([[got[k]["prob"], got[k]["postMean"], got[k]["mapTime"]] for k in common])
+        w = np.array([want[k][0] for k in common])
+        np.testing.assert_allclose(g[:, 0], w[:, 0], rtol=REL_TOL, err_msg=label)
+        np.testing.assert_allclose(g[:, 1], w[:, 1], rtol=REL_TOL, err_msg=label)
+        assert (g[:, 2] != w[:, 2]).mean() < 5e-3, label
+        # and against the dense kernel
+        both = sorted(set(gd) & set(got))
+        assert len(both) >= 0.995 * max(len(gd), len(got))
+        np.testing.assert_allclose([got[k]["postMean"] for k in both], [gd[k]["postMean"] for k in both], rtol=REL_TOL)
+        assert np.mean([got[k]["mapState"] != gd[k]["mapState"] for k in both]) < 5e-3
+    # the segment list itself does not depend on the block size or on the re-run
+    assert set(results["default"]) == set(results["blocks of 8"]) == set(results["blocks of 32"]) == set(results["item overflow"])
+
+
+def test_sparse_age_estimates_ragged_windows(synthetic69, monkeypatch):
+    """Windows that start and end inside checkpoint blocks, scan windows narrower than the decode windows, a partially
+    filled tile and windows shorter than a block: sparse path (forced) vs the dense kernel."""
+    from fastsmc_b200 import _native as N
+    o, ctx = synthetic69
+    rng = np.random.default_rng(21)
+    a, b = _pairs(rng, 32 * 39 + 5, o.num_haps)
+    nb = (len(a) + 31) // 32
+    win = np.array([[0, o.sites], [5, 37], [31, 33], [100, 2999], [1000, 1001], [777, 2222], [64, 96], [1, 3000]] * 5, np.int32)[:nb]
+    scan = np.array([[0, o.sites], [6, 30], [31, 33], [500, 2500], [1000, 1001], [800, 2200], [64, 96], [33, 2990]] * 5, np.int32)[:nb]
+    tiles = ctx.make_tiles(a, b, windows=win, scan=scan, sites=o.sites)
+    flags = N.CALL_SEGMENTS | N.SEG_AGE
+    dense = ctx.decode(tiles, flags | N.WIDE_KERNEL, segment_capacity=1 << 18)
+    monkeypatch.setenv("FSMC_SPARSE", "1")
+    sparse = ctx.decode(tiles, flags, segment_capacity=1 << 18)
+    assert sparse.stats.sparseKernel == 1 and dense.stats.sparseKernel == 0
+    gd, gs = {_seg_key(s): s for s in dense.segments}, {_seg_key(s): s for s in sparse.segments}
+    both = sorted(set(gd) & set(gs))
+    assert len(both) >= 0.99 * max(len(gd), len(gs)) and len(both) > 20
+    for f in ("prob", "postMean"):
+        np.testing.assert_allclose([gs[k][f] for k in both], [gd[k][f] for k in both], rtol=REL_TOL)
+    assert np.mean([gs[k]["mapState"] != gd[k]["mapState"] for k in both]) < 1e-2
