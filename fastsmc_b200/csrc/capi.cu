@@ -320,6 +320,14 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bo
   }
   return {};
 }
+bool sparsePreferred(const double meanScanSites)
+{
+  if (const char* e = std::getenv("FSMC_SPARSE")) {
+    return std::atoi(e) != 0;
+  }
+  return meanScanSites >= 2000.0;
+}
+
 size_t fastSmemBytes(const FastChoice& fc, const int S)
 {
   if (fc.splitWarps > 0) {
@@ -540,6 +548,25 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, const int64_t numHa
   return FSMC_OK;
 }
 
+int fsmc_query_kernel(fsmc_ctx* ctx, const uint32_t flags, const double meanScanSites, fsmc_kernel_info* out)
+{
+  if (!ctx || !out) {
+    return fail(FSMC_E_INVALID, "fsmc_query_kernel: NULL argument");
+  }
+  if (!ctx->hasModel) {
+    return fail(FSMC_E_STATE, "fsmc_query_kernel: set the model first");
+  }
+  const DeviceModel& m = ctx->model;
+  const FastChoice fc = chooseFastKernel(m, flags, sparsePreferred(meanScanSites));
+  const KernelChoice kc = chooseKernel(m.S, flags);
+  out->statesKernel = fc.fn ? m.S : kc.statesKernel;
+  out->narrowKernel = fc.narrow ? 1 : 0;
+  out->sparseKernel = fc.sparse ? 1 : 0;
+  out->tileWarps = fc.splitWarps > 0 ? fc.splitWarps : 1;
+  out->largeScratch = (!fc.fn || !fc.narrow || fc.sparse) ? 1 : 0;
+  return FSMC_OK;
+}
+
 int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** out)
 {
   if (!ctx || !req || !out) {
@@ -564,6 +591,9 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     return fail(FSMC_E_INVALID, "fsmc_plan_create: NULL input array");
   }
   const DeviceModel& m = ctx->model;
+  if (ctx->sites != m.L) {
+    return fail(FSMC_E_STATE, "fsmc_plan_create: the haplotypes have %lld sites, the model %d", static_cast<long long>(ctx->sites), m.L);
+  }
   long long maxLen = 0;
   double pairSites = 0.0, scanSites = 0.0;
   for (long long t = 0; t < T; ++t) {
@@ -673,10 +703,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   // Sparse age estimates pay off when IBD runs cover a small part of the scan windows: whole-chromosome windows
   // (all-pairs decoding, hashing off).  The windows of hashing candidates lie mostly inside runs: dense kernel.
   // FSMC_SPARSE=0/1 overrides the window-length rule (development / tests).
-  bool preferSparse = T > 0 && scanSites / static_cast<double>(T) >= 2000.0;
-  if (const char* e = std::getenv("FSMC_SPARSE")) {
-    preferSparse = std::atoi(e) != 0;
-  }
+  const bool preferSparse = T > 0 && sparsePreferred(scanSites / static_cast<double>(T));
   const FastChoice fc = chooseFastKernel(m, flags, preferSparse);
   plan->fast = fc.fn != nullptr;
   plan->sparse = fc.sparse;

@@ -80,6 +80,11 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
   if (decodingParams.decodingSequence) {
     throw std::runtime_error("sequence mode is not supported by the B200 build (array mode only)");
   }
+  if (!decodingParams.expectedCoalTimesFile.empty()) {
+    // ref: HMM.cpp updateOutputStructures / readExpectedTimesFromIntervalsFile — not implemented: fail instead of silently
+    // using the decoding quantities' expected times
+    throw std::runtime_error("expectedCoalTimesFile is not supported by the B200 build (expected times come from the decoding quantities)");
+  }
   m_batchSize = decodingParams.batchSize;
   sequenceLength = data.sites;
   m_model = buildModelTables(data, m_decodingQuant, decodingParams);
@@ -471,14 +476,25 @@ void HMM::flushPending(const bool all)
     return;
   }
   const bool segments = decodingParams.FastSMC;
+  const bool store = m_storePerPairPosteriorMean || m_storePerPairMAP || m_storePerPairPosterior || m_storeSumOfPosterior;
   if (segments) {
     runSegmentChunk(m_pending.data(), n);
-  } else if (m_storePerPairPosteriorMean || m_storePerPairMAP || m_storePerPairPosterior || m_storeSumOfPosterior) {
-    runPerSiteChunk(m_pending.data(), m_pendingRow.data(), n);
-    m_pendingRow.erase(m_pendingRow.begin(), m_pendingRow.begin() + n);
-  } else if (decodingParams.doPosteriorSums || decodingParams.doMajorMinorPosteriorSums) {
-    runPosteriorSumChunk(m_pending.data(), n);
+  } else {
+    // ref: HMM.cpp:570-581 (addToBatch) — the sums over pairs and the per-pair outputs are independent consumers of the
+    // same batch: both run when both are asked for
+    if (store) {
+      if (m_pendingRow.size() < n) {
+        // pairs queued by decodeAll / decodePair while the store flags of an earlier ASMC::decodePairs are still set: the
+        // return structure has no rows for them (the reference throws std::out_of_range from its .at() here)
+        throw std::out_of_range("HMM: per-pair outputs are stored but the return structure was not initialised for these pairs");
+      }
+      runPerSiteChunk(m_pending.data(), m_pendingRow.data(), n);
+    }
+    if (decodingParams.doPosteriorSums || decodingParams.doMajorMinorPosteriorSums) {
+      runPosteriorSumChunk(m_pending.data(), n);
+    }
   }
+  m_pendingRow.erase(m_pendingRow.begin(), m_pendingRow.begin() + static_cast<long>(std::min(n, m_pendingRow.size())));
   m_pending.erase(m_pending.begin(), m_pending.begin() + n);
 }
 
@@ -585,8 +601,13 @@ void HMM::startDecodeWorkers()
 {
   m_pipeline = std::make_unique<DecodePipeline>();
   const bool ages = decodingParams.doPerPairPosteriorMean || decodingParams.doPerPairMAP;
-  const bool narrow = !decodingParams.exactArithmetic && (!ages || m_model.ageThreshold <= m_model.stateThreshold);
-  int workers = narrow ? 2 : 1;
+  // Two contexts only when the device layer says the request's kernel keeps its scratch small (narrow records): the
+  // full-beta kernels and the checkpointed path size theirs from the free device memory, one context per device.
+  fsmc_kernel_info info{};
+  check(fsmc_query_kernel(m_ctx, FSMC_CALL_SEGMENTS | (ages ? FSMC_SEG_AGE : 0u) | (decodingParams.exactArithmetic ? FSMC_EXACT : 0u),
+                          m_windowed ? 0.0 : static_cast<double>(data.sites), &info),
+        "fsmc_query_kernel");
+  int workers = info.largeScratch ? 1 : 2;
   if (const char* e = std::getenv("FSMC_DECODE_WORKERS")) {  // development / A-B runs
     workers = std::max(1, std::min(2, std::atoi(e)));
   }

@@ -10,6 +10,7 @@
 #include <atomic>
 #include <cstdint>
 #include <memory>
+#include <stdexcept>
 #include <string>
 #include <vector>
 
@@ -92,9 +93,23 @@ public:
   const Data& getData() const { return data; }
 
   void setStorePerPairPosteriorMean(bool v = true) { m_storePerPairPosteriorMean = v; }
-  void setWritePerPairPosteriorMean(bool v = true) { m_writePerPairPosteriorMean = v; }
+  // the per-pair text writers of ASMC_exe (.perPairPosteriorMeans.gz / .perPairMAP.gz) are not part of this build: asking for
+  // them fails loudly instead of silently producing no file (use ASMC::decodePairs and the returned arrays)
+  void setWritePerPairPosteriorMean(bool v = true)
+  {
+    if (v) {
+      throw std::runtime_error("writing .perPairPosteriorMeans.gz is not supported by the B200 build; use the stored per-pair outputs");
+    }
+    m_writePerPairPosteriorMean = v;
+  }
   void setStorePerPairMap(bool v = true) { m_storePerPairMAP = v; }
-  void setWritePerPairMap(bool v = true) { m_writePerPairMAP = v; }
+  void setWritePerPairMap(bool v = true)
+  {
+    if (v) {
+      throw std::runtime_error("writing .perPairMAP.gz is not supported by the B200 build; use the stored per-pair outputs");
+    }
+    m_writePerPairMAP = v;
+  }
   void setStorePerPairPosterior(bool v = true) { m_storePerPairPosterior = v; }
   void setStoreSumOfPosterior(bool v = true) { m_storeSumOfPosterior = v; }
 

@@ -93,8 +93,11 @@ public:
       deflateBlock("", 0, mLevel, o);
       std::fwrite(o.data(), 1, o.size(), mFile);
     }
-    std::fclose(mFile);
+    const bool closeFailed = std::fclose(mFile) != 0;  // a late write error (disk full) surfaces here
     mFile = nullptr;
+    if (closeFailed && !mError) {
+      mError = std::make_exception_ptr(std::runtime_error("OutputPipeline: error closing the output file (write failed)"));
+    }
     if (mError) {
       std::rethrow_exception(mError);
     }

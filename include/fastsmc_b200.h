@@ -175,6 +175,19 @@ typedef struct fsmc_decode_stats {
 
 int fsmc_decode(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_decode_stats* stats);
 
+/* Which kernel family a request with these flags would run on the context's model, before any request exists: callers
+ * that run several contexts on one device (HMM's pipelined decode workers) must know whether the request sizes its
+ * scratch for the whole device.  meanScanSites = expected length of the scan windows (0 for hashing candidates): the
+ * sparse age-estimate path is chosen for long windows only.                                                         */
+typedef struct fsmc_kernel_info {
+  int32_t statesKernel;  /* as fsmc_decode_stats                                                   */
+  int32_t narrowKernel;
+  int32_t sparseKernel;
+  int32_t tileWarps;
+  int32_t largeScratch;  /* 1: scratch grows with free device memory (full beta rows or checkpoints): one context per device */
+} fsmc_kernel_info;
+int fsmc_query_kernel(fsmc_ctx* ctx, uint32_t flags, double meanScanSites, fsmc_kernel_info* out);
+
 /* Split-phase form of the same call, for callers that keep inputs resident in HBM and overlap host
  * work with the kernels (and for timing the kernels without host traffic):
  *   fsmc_plan_create  : validates the request, copies its input arrays to the device, allocates

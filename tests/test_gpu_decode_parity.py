@@ -463,3 +463,92 @@ def test_sparse_age_estimates_ragged_windows(synthetic69, monkeypatch):
     for f in ("prob", "postMean"):
         np.testing.assert_allclose([gs[k][f] for k in both], [gd[k][f] for k in both], rtol=REL_TOL)
     assert np.mean([gs[k]["mapState"] != gd[k]["mapState"] for k in both]) < 1e-2
+
+
+# ---- BASELINE.json configs[1] at its own shape: 1 000 haplotypes x 10 000 SNPs, S = 69 -----------------------------------
+
+
+def test_cfg2_shape_batches_against_oracle(oracle_mod, tmp_path):
+    """64 reference batches spread over cfg2's 15 610 (the last, partially filled one included), all 10 000 sites: the
+    oracle's per-site posteriors vs (a) the per-site IBD probability of decodeNarrowKernel, (b) the segments of the sparse
+    all-state path (the bench's headline) and of the narrow kernel (FastSMC_exe default flags): per-site levels equal
+    except within 1e-4 of a threshold, segment scores within 1e-4, (c) posterior mean / MAP of the segments from the
+    oracle's full posterior matrices for a sample of pairs."""
+    import sys
+    from concurrent.futures import ThreadPoolExecutor
+    from conftest import DQ_69, ROOT
+    from fastsmc_b200 import _native as N, synth
+    sys.path.insert(0, ROOT)
+    import bench
+    root = str(tmp_path / "cfg2")
+    synth.dataset(root, bench.N_HAPS, bench.N_SITES, bench.SPAN_BP, bench.CHROM, bench.SEED)
+    kw = dict(hashing=False, time=50, doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
+    o = oracle_mod.Oracle(root, DQ_69, str(tmp_path / "o"), noConditionalAgeEstimates=True, **kw)
+    o_cond = oracle_mod.Oracle(root, DQ_69, str(tmp_path / "oc"), noConditionalAgeEstimates=False, **kw)
+    L = o.sites
+    a_all, b_all = bench.all_pairs_in_reference_order(o.num_haps // 2)
+    n_batches = (len(a_all) + 31) // 32
+    assert n_batches == 15610 and len(a_all) % 32 == 12
+    picked = np.unique(np.r_[np.linspace(0, n_batches - 1, 63).astype(int), n_batches - 1])
+    idx = np.concatenate([np.arange(32 * t, min(32 * (t + 1), len(a_all))) for t in picked])
+    a, b = a_all[idx], b_all[idx]
+    # the oracle's per-site IBD probability of every picked pair (host threads; the oracle call releases the GIL)
+    chunks = [np.arange(i, min(i + 32, len(a))) for i in range(0, len(a), 32)]
+    with ThreadPoolExecutor(8) as pool:
+        parts = list(pool.map(lambda c: o.decode_summary(a[c], b[c], 0, L, mean=False, map_=False)[2], chunks))
+    ibd = np.concatenate(parts)
+    thr = np.float32(o.probability_threshold) * np.array([1000, 100, 10, 1], np.float32)
+    level = np.full(ibd.shape, -1, np.int8)
+    for i in (3, 2, 1, 0):
+        level[ibd >= thr[i]] = i
+    ambiguous = np.zeros(ibd.shape, bool)
+    for t in thr:
+        ambiguous |= np.abs(ibd - t) <= REL_TOL * t
+
+    def check_segments(ctx, label):
+        tiles = ctx.make_tiles(a, b, sites=L)
+        rows = tiles["rows"]
+        row_of_pair = {int(r): i for i, r in enumerate(rows)}
+        r = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE, segment_capacity=1 << 18)
+        mine = np.full(ibd.shape, -1, np.int8)
+        score_err = 0.0
+        for s in r.segments:
+            i = row_of_pair[int(s["pair"])]
+            lo, hi = int(s["posStart"]), int(s["posEnd"]) + 1
+            mine[i, lo:hi] = int(s["level"])
+            if not ambiguous[i, max(lo - 1, 0):hi + 1].any():  # same segment in the oracle: compare the score
+                want = float(ibd[i, lo:hi].astype(np.float64).sum())
+                score_err = max(score_err, abs(float(s["prob"]) - want) / want)
+        bad = (mine != level) & ~ambiguous
+        assert not bad.any(), f"{label}: {int(bad.sum())} sites with a different level away from the thresholds"
+        assert score_err < REL_TOL, label
+        assert len(r.segments) > 1500
+        return r, row_of_pair
+
+    ctx = context_from_oracle(o, oracle_mod)
+    r_sparse, row_of_pair = check_segments(ctx, "sparse")
+    assert r_sparse.stats.sparseKernel == 1
+    ctx_cond = context_from_oracle(o_cond, oracle_mod)
+    r_narrow, _ = check_segments(ctx_cond, "narrow")
+    assert r_narrow.stats.narrowKernel == 1 and r_narrow.stats.sparseKernel == 0
+    tiles = ctx_cond.make_tiles(a, b, sites=L)
+    site = ctx_cond.decode(tiles, N.SITE_IBD)
+    assert site.stats.narrowKernel == 1
+    np.testing.assert_allclose(site.site_ibd[tiles["rows"]], ibd, rtol=REL_TOL, atol=1e-12)
+
+    # (c) age estimates: full posterior of the pairs that hold the 40 longest segments
+    seg = r_sparse.segments
+    longest = seg[np.argsort(seg["posEnd"] - seg["posStart"])[-40:]]
+    exp_t, prior = o.vector("expectedTimes"), o.vector("initialStateProb")
+    for s in longest:
+        i = row_of_pair[int(s["pair"])]
+        lo, hi = int(s["posStart"]), int(s["posEnd"]) + 1
+        if ambiguous[i, max(lo - 1, 0):hi + 1].any():
+            continue
+        post = o.decode_posterior(a[i:i + 1], b[i:i + 1], 0, L)[0]  # [site][state]
+        sums = post[lo:hi].astype(np.float64).sum(axis=0)
+        want_mean = float((sums / sums.sum() * exp_t).sum())
+        assert abs(float(s["postMean"]) - want_mean) <= REL_TOL * want_mean
+        ratio = sums / prior
+        best = int(np.argmax(ratio))
+        assert int(s["mapState"]) == best or ratio[int(s["mapState"])] >= ratio[best] * (1 - 1e-3)
