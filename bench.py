@@ -36,6 +36,8 @@ DQ = os.path.join(ROOT, "data", "30-100-2000.decodingQuantities.gz")
 FLOPS_PER_PAIR_SITE_STATE = 35  # 15 forward + 15 backward + 3 combine + 2 consume
 NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE = (6.072805e9 + 6.078759e9) / (37888 * 10000)  # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt
 NCU_DRAM_BYTES_PER_PAIR_SITE = (109.922461e9 + 109.458343e9) / (37888 * 10000)  # profiles/r1_v4_decodeFast_s69_ncu_full.txt
+# profiles/r2_v4_decodeNarrowSparse_ncu_full.txt: 90.32 GB read + 129.04 GB written by one launch over cfg2 (blocks of 32 sites)
+NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE = (90.323012e9 + 129.044333e9) / (499500 * 10000)
 WORKLOAD = "cfg2: all-pairs, hashing off, 1000 haplotypes x 10000 SNPs, S=69 (30-100-2000), time=50, batchSize=32"
 
 
@@ -279,7 +281,9 @@ def jobs_run(asmc, rank, world, local, dist):
             "pair_sites": sum(r.pairSites for r in reports), "candidates": sum(r.candidates for r in reports),
             "segments": sum(r.segments for r in reports),
             "decode_kernel_s": sum(r.kernelMs for r in reports) / 1e3, "seed_kernel_s": sum(r.seedMs for r in reports) / 1e3,
-            "host_prepare_s": sum(r.prepareSeconds for r in reports), "host_seed_call_s": sum(r.seedSeconds for r in reports),
+            "host_prepare_s": sum(r.prepareSeconds for r in reports), "host_prepare_cut_s": sum(r.cutSeconds for r in reports),
+            "host_prepare_tables_s": sum(r.tablesSeconds for r in reports), "host_prepare_upload_s": sum(r.uploadSeconds for r in reports),
+            "host_seed_call_s": sum(r.seedSeconds for r in reports),
             "host_order_s": sum(r.orderSeconds for r in reports), "host_decode_calls_s": sum(r.decodeSeconds for r in reports),
             "host_output_s": sum(r.outputSeconds for r in reports)}
     if dist:
@@ -389,6 +393,8 @@ def main():
     n_segments = int(r.stats.numSegments)
     scratch_bytes = int(r.stats.scratchBytes)
     launches_per_step = int(r.stats.kernelLaunches)
+    sparse = {"on": bool(r.stats.sparseKernel), "block_sites": int(r.stats.checkpointSites), "items": int(r.stats.sparseItems),
+              "checkpoint_bytes": int(r.stats.checkpointBytes)}
     plan.close()
     total_ms = max_over_ranks(total_ms, world)
     ms_per_step = total_ms / args.steps
@@ -461,13 +467,36 @@ def main():
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
         kernel_ms = float(np.mean(per_step))
-        # algorithmic HBM bytes per pair-site of this kernel design: the backward sweep writes beta[S] floats and the
-        # forward sweep reads them back (8*S), plus 2 bits of genotype input per pair-site (0.25 B)
-        bytes_per_pair_site = 8.0 * S + 0.25
-        achieved = my_pair_sites * bytes_per_pair_site / (kernel_ms / 1e3) / 1e9  # rank 0's launches
         prop = torch.cuda.get_device_properties(local)
         fp32_peak = prop.multi_processor_count * 128 * 2 * 1.965e9 / 1e12
         fp32_achieved = my_pair_sites * FLOPS_PER_PAIR_SITE_STATE * S / (kernel_ms / 1e3) / 1e12
+        if sparse["on"]:
+            # decode_sparse.cuh: narrow sweeps + beta checkpoints + refinement of the IBD runs.  Algorithmic HBM bytes per
+            # pair-site: 2 genotype bits, the narrow record written by the backward and read by the forward sweep
+            # (2 x 16 B), one full beta vector (Spad floats) per block of `block_sites` sites
+            bytes_per_pair_site = 0.25 + 32.0 + 4.0 * ((S + 3) // 4 * 4) / sparse["block_sites"]
+            kernel_name = "decodeNarrowKernel<69, sparse> (+ refineKernel<69>, finalizeSegmentsKernel: ~6 % of the step)"
+            ncu_bytes = NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE
+            traffic_src = "ncu --set full capture of the kernel in this bench (profiles/r2_*_decodeNarrowSparse_ncu_full.txt)"
+        else:
+            # the backward sweep writes beta[S] floats and the forward sweep reads them back (8*S) + 2 genotype bits
+            bytes_per_pair_site = 8.0 * S + 0.25
+            kernel_name = "decodeFastKernel<69>"
+            ncu_bytes = NCU_DRAM_BYTES_PER_PAIR_SITE
+            traffic_src = "ncu --set full capture of a 37888-pair launch (profiles/r1_v4_decodeFast_s69_ncu_full.txt), scaled by pair-sites"
+        achieved = my_pair_sites * bytes_per_pair_site / (kernel_ms / 1e3) / 1e9  # rank 0's launches
+        hbm_roofline = {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s", "frac": achieved / hbm_peak,
+                        "traffic": ncu_bytes * my_pair_sites, "traffic_source": traffic_src,
+                        "algorithmic_bytes": bytes_per_pair_site * my_pair_sites, "peak_source": peak_src,
+                        "algorithmic_bytes_per_pair_site": bytes_per_pair_site}
+        fp32_roofline = {"bound": "fp32", "achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": fp32_achieved / fp32_peak, "traffic": ncu_bytes * my_pair_sites, "traffic_source": traffic_src,
+                         "flops_per_pair_site": FLOPS_PER_PAIR_SITE_STATE * S,
+                         "flops_source": "SURVEY.md 8(d): 35 x S algorithmic flops of the reference's recurrences per pair-site",
+                         "peak_source": "SMs x 128 lanes x 2 x 1.965 GHz (nominal FP32 pipe; no tensor-core work on this path)"}
+        # the kernel's binding roofline comes first: FP32 pipe for the sparse path, HBM for the kernel that streams beta
+        roofline = dict(fp32_roofline if sparse["on"] else hbm_roofline, kernel=kernel_name, kernel_ms=kernel_ms)
+        other = dict(hbm_roofline if sparse["on"] else fp32_roofline)
         line = {
             "metric": "hmm_pair_sites_per_s", "value": value, "unit": "pair-sites/s", "n_gpus": world, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong",
@@ -477,23 +506,10 @@ def main():
                        "segments_per_step": n_segments,
                        "flags": "segment length + per-segment posterior mean + MAP over ALL states (noConditionalAgeEstimates), "
                                 "the reference's regression-test / FastSMC-constructor defaults",
-                       "l2": f"no flush needed: each step streams {scratch_bytes / 2**30:.0f} GiB of backward-sweep scratch "
-                             "through HBM (>> 126 MB L2)", "parallelism": f"the job's {(len(a) + 31) // 32} reference batches dealt to {world} GPU(s) in contiguous shares; "
+                       "l2": f"no flush needed: each step streams {(scratch_bytes + sparse['checkpoint_bytes']) / 2**30:.0f} GiB of "
+                             "backward-sweep records / checkpoints through HBM (>> 126 MB L2)", "parallelism": f"the job's {(len(a) + 31) // 32} reference batches dealt to {world} GPU(s) in contiguous shares; "
                                       "no collective on the data path"},
-            "roofline": {"bound": "hbm", "achieved": achieved, "peak": hbm_peak, "unit": "GB/s",
-                         "frac": achieved / hbm_peak,
-                         # DRAM bytes per launch: dram__bytes_read.sum + dram__bytes_write.sum of the ncu --set full
-                         # capture (profiles/r1_v4_decodeFast_s69_ncu_full.txt: 219.38 GB for 37 888 pairs x 10 000
-                         # sites = 579.0 B per pair-site, the padding of 69 states to 72 included), scaled to this
-                         # launch's pair-sites
-                         "traffic": NCU_DRAM_BYTES_PER_PAIR_SITE * my_pair_sites,
-                         "traffic_source": "ncu --set full capture of a 37888-pair launch, scaled by pair-sites",
-                         "algorithmic_bytes": bytes_per_pair_site * my_pair_sites, "peak_source": peak_src,
-                         "kernel": "decodeFastKernel<69>", "kernel_ms": kernel_ms,
-                         "algorithmic_bytes_per_pair_site": bytes_per_pair_site},
-            "roofline_fp32": {"achieved": fp32_achieved, "peak": fp32_peak, "unit": "TFLOP/s", "frac": fp32_achieved / fp32_peak,
-                              "flops_per_pair_site": FLOPS_PER_PAIR_SITE_STATE * S,
-                              "peak_source": "SMs x 128 lanes x 2 x 1.965 GHz (nominal)"},
+            "roofline": roofline, ("roofline_hbm" if sparse["on"] else "roofline_fp32"): other, "sparse_age_estimates": sparse,
             "default_flags": dict(narrow, roofline={"bound": "fp32", "achieved": my_pair_sites / (narrow_rank0_ms / 1e3) * FLOPS_PER_PAIR_SITE_STATE * S / 1e12,
                                                      "peak": fp32_peak, "unit": "TFLOP/s",
                                                      "frac": my_pair_sites / (narrow_rank0_ms / 1e3) * FLOPS_PER_PAIR_SITE_STATE * S / 1e12 / fp32_peak,

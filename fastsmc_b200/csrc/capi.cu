@@ -127,6 +127,8 @@ struct fsmc_ctx {
   DevBuf<uint64_t> haps;
   long long numHaps = 0;
   DevBuf<float> scratch, accScratch;
+  DevBuf<float> stageE1, stageE0, stageE2, stageD, stageB, stageU, stageR;  // fsmc_set_model staging
+  DevBuf<int> stageRowIdx;
   DevBuf<float> ckptBeta;  // sparse age estimates: beta checkpoints of every tile of the current plan (decode_sparse.cuh)
   std::vector<float> hostPrior, hostExpTimes, hostColRatios;
   long long sites = 0;
@@ -462,9 +464,12 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
   const int Spad = (S + 3) / 4 * 4;
   cudaStream_t st = ctx->stream;
 
-  // staging copies of the caller's tables, gathered into per-site rows on the device
-  DevBuf<float> e1, e0, e2, D, B, U, R;
-  DevBuf<int> rowIdx;
+  // staging copies of the caller's tables, gathered into per-site rows on the device.  The staging buffers belong to the
+  // context (grow-only): cudaFree synchronises the whole device, which stalls the other host thread of a GPU that runs
+  // the jobs of a data set two at a time.
+  DevBuf<float>&e1 = ctx->stageE1, &e0 = ctx->stageE0, &e2 = ctx->stageE2, &D = ctx->stageD, &B = ctx->stageB, &U = ctx->stageU,
+  &R = ctx->stageR;
+  DevBuf<int>& rowIdx = ctx->stageRowIdx;
   const size_t nE = static_cast<size_t>(L) * S, nT = static_cast<size_t>(mdl->numDistances) * S;
   FSMC_CUDA(e1.ensure(nE));
   FSMC_CUDA(e0.ensure(nE));

@@ -160,6 +160,7 @@ Data Data::forJob(const Data& whole, const DecodingParams& params)
   d.flipMask = whole.flipMask;
   d.totalSamplesCount = whole.totalSamplesCount;
   d.derivedAlleleCounts = whole.derivedAlleleCounts;
+  d.mUndistinguished = whole.mUndistinguished;  // same whole-file counts -> same draws
   d.setJobGeometry(params);
   if (d.foldToMinorAlleles != whole.foldToMinorAlleles) {
     throw std::runtime_error("Data::forJob: folding differs between the source and the job");
@@ -550,6 +551,18 @@ Individual Data::individual(const unsigned long i) const
 // in the reference's order.  The shuffles themselves only depend on their seed and run on all host threads (at UK
 // Biobank scale they are 3 x sites shuffles of ~10^6 shorts).
 std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int numCsfsSamples) const
+{
+  UndistinguishedCache& cache = *mUndistinguished;
+  std::lock_guard<std::mutex> g(cache.lock);
+  if (cache.csfsSamples != numCsfsSamples || cache.knownSeed != mUseKnownSeed) {
+    cache.counts = drawUndistinguishedCounts(numCsfsSamples);
+    cache.csfsSamples = numCsfsSamples;
+    cache.knownSeed = mUseKnownSeed;
+  }
+  return cache.counts;
+}
+
+std::vector<std::vector<int>> Data::drawUndistinguishedCounts(const int numCsfsSamples) const
 {
   std::vector<std::vector<int>> counts(sites, std::vector<int>(3, 0));
   struct Draw {

@@ -5,6 +5,8 @@
 #pragma once
 
 #include <cstdint>
+#include <memory>
+#include <mutex>
 #include <string>
 #include <utility>
 #include <vector>
@@ -105,6 +107,17 @@ private:
                bool subset);
   void flushSiteWord();
   void finishSites(int numSites);
+  // calculateUndistinguishedCounts depends on the WHOLE file's allele counts, the seed and the CSFS sample count only, not on
+  // the job's sample subset: the jobs cut out of one data set (forJob) share the result instead of re-drawing it
+  // (3 x sites shuffles of 2N shorts, the dominant per-job host cost at 64 jobs per data set).
+  struct UndistinguishedCache {
+    std::mutex lock;
+    int csfsSamples = -1;
+    bool knownSeed = false;
+    std::vector<std::vector<int>> counts;
+  };
+  mutable std::shared_ptr<UndistinguishedCache> mUndistinguished = std::make_shared<UndistinguishedCache>();
+  std::vector<std::vector<int>> drawUndistinguishedCounts(int numCsfsSamples) const;
   std::vector<uint64_t> mWordBuf;    // bits of the current 64-site word, one entry per loaded haplotype
   std::vector<uint64_t> mWordMajor;  // completed words, [word][hap]; transposed into hapBits by finishSites
   long mWordBufIndex = -1;

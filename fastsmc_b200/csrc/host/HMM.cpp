@@ -59,6 +59,48 @@ void appendInt(std::string& s, const long v)
 
 }  // namespace
 
+namespace
+{
+// Device contexts outlive the HMM that used them: the jobs of one data set (runJobs) create one HMM after the other on the
+// same device, and a context's buffers (scratch slabs, seeding tables, sort buffers: grow-only) and its stream are what
+// is expensive to set up.  A released context keeps its device memory until the process ends.
+class ContextPool
+{
+public:
+  fsmc_ctx* acquire(const int device)
+  {
+    {
+      std::lock_guard<std::mutex> g(mLock);
+      auto& idle = mIdle[device];
+      if (!idle.empty()) {
+        fsmc_ctx* ctx = idle.back();
+        idle.pop_back();
+        return ctx;
+      }
+    }
+    fsmc_ctx* ctx = nullptr;
+    check(fsmc_ctx_create(device, &ctx), "fsmc_ctx_create");
+    return ctx;
+  }
+  void release(const int device, fsmc_ctx* ctx)
+  {
+    if (ctx) {
+      std::lock_guard<std::mutex> g(mLock);
+      mIdle[device].push_back(ctx);
+    }
+  }
+
+private:
+  std::mutex mLock;
+  std::map<int, std::vector<fsmc_ctx*>> mIdle;
+};
+ContextPool& contextPool()
+{
+  static ContextPool* pool = new ContextPool;  // never destroyed: no CUDA calls during static destruction
+  return *pool;
+}
+}  // namespace
+
 struct HMM::GzOut {
   OutputPipeline writer;
   std::vector<std::string> idPrefix;  // "fam\tiid\t" per individual (text output)
@@ -87,7 +129,9 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
   }
   m_batchSize = decodingParams.batchSize;
   sequenceLength = data.sites;
+  const double tTables = now();
   m_model = buildModelTables(data, m_decodingQuant, decodingParams);
+  m_stats.tablesWallS = now() - tTables;
   stateThreshold = static_cast<unsigned>(m_model.stateThreshold);
   ageThreshold = static_cast<unsigned>(m_model.ageThreshold);
   probabilityThreshold = m_model.probabilityThreshold;
@@ -109,7 +153,9 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
   if (const char* e = std::getenv("FSMC_FLUSH_BATCHES")) {  // development: reference batches per decode call
     m_flushPairs = static_cast<size_t>(m_batchSize) * static_cast<size_t>(std::max(1, std::atoi(e)));
   }
+  const double tUpload = now();
   uploadModel();
+  m_stats.uploadWallS = now() - tUpload;
 }
 
 // ref: HMM.cpp:504-513
@@ -243,7 +289,7 @@ void HMM::uploadModel()
 void HMM::uploadModelTo(fsmc_ctx*& ctx)
 {
   fsmc_ctx*& m_ctx = ctx;  // the body below fills whichever context it is given
-  check(fsmc_ctx_create(decodingParams.device, &m_ctx), "fsmc_ctx_create");
+  m_ctx = contextPool().acquire(decodingParams.device);
   fsmc_model m{};
   m.states = m_model.states;
   m.sites = m_model.sites;
@@ -589,12 +635,8 @@ HMM::~HMM()
       w.join();
     }
   }
-  if (m_ctx2) {
-    fsmc_ctx_destroy(m_ctx2);
-  }
-  if (m_ctx) {
-    fsmc_ctx_destroy(m_ctx);
-  }
+  contextPool().release(decodingParams.device, m_ctx2);
+  contextPool().release(decodingParams.device, m_ctx);
 }
 
 void HMM::startDecodeWorkers()

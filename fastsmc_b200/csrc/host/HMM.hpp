@@ -133,6 +133,8 @@ public:
     double deviceMs = 0.0;    // device time of the fsmc_decode calls incl. their copies
     double decodeWallS = 0.0; // host wall time spent in fsmc_decode
     double outputWallS = 0.0; // host wall time formatting + compressing records
+    double tablesWallS = 0.0; // constructor: decoding quantities + emission / transition tables on the host
+    double uploadWallS = 0.0; // constructor: context creation, model and haplotype upload
   };
   const RunStats& getRunStats() const { return m_stats; }
   fsmc_ctx* context() { return m_ctx; }

@@ -75,8 +75,12 @@ std::vector<JobReport> runJobs(const DecodingParams& params, const Data& whole, 
         p.verbose = false;
         // reading, model preparation and decoding of different jobs overlap freely: the only process-wide state, the
         // std::rand sequence of the emission preparation, is seeded and consumed under its own lock (Data.cpp)
-        auto job = std::make_unique<FastSMC>(p, Data::forJob(whole, p));
+        Data cut = Data::forJob(whole, p);
+        rep.cutSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        auto job = std::make_unique<FastSMC>(p, std::move(cut));
         rep.prepareSeconds = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+        rep.tablesSeconds = job->hmm().getRunStats().tablesWallS;
+        rep.uploadSeconds = job->hmm().getRunStats().uploadWallS;
         job->run();
         const HMM::RunStats& st = job->hmm().getRunStats();
         rep.candidates = job->getSeedingStats().candidates;

@@ -32,6 +32,7 @@ struct JobReport {
   // host wall time of the job's stages: cutting the job's samples out of the data set + model tables + upload,
   // fsmc_seed, candidate order, fsmc_decode calls, record formatting/compression
   double prepareSeconds = 0.0, seedSeconds = 0.0, orderSeconds = 0.0, decodeSeconds = 0.0, outputSeconds = 0.0;
+  double cutSeconds = 0.0, tablesSeconds = 0.0, uploadSeconds = 0.0;  // parts of prepareSeconds
   std::string error;       // empty on success
 };
 

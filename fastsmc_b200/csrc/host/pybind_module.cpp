@@ -397,6 +397,9 @@ PYBIND11_MODULE(pyASMC, m)
       .def_readonly("seedMs", &ASMC::JobReport::seedMs)
       .def_readonly("wallSeconds", &ASMC::JobReport::wallSeconds)
       .def_readonly("prepareSeconds", &ASMC::JobReport::prepareSeconds)
+      .def_readonly("cutSeconds", &ASMC::JobReport::cutSeconds)
+      .def_readonly("tablesSeconds", &ASMC::JobReport::tablesSeconds)
+      .def_readonly("uploadSeconds", &ASMC::JobReport::uploadSeconds)
       .def_readonly("seedSeconds", &ASMC::JobReport::seedSeconds)
       .def_readonly("orderSeconds", &ASMC::JobReport::orderSeconds)
       .def_readonly("decodeSeconds", &ASMC::JobReport::decodeSeconds)
