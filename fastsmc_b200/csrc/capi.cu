@@ -111,6 +111,7 @@ struct SeedKey {
   int32_t gap;
   float minLengthCm;
   uint64_t genPosSum, globalIdSum, flipSum;  // checksums of the callers' arrays (contents, not addresses)
+  float skip;
   uint32_t window[4];
   int32_t lastJob, aboveDiag;
   uint32_t flags;
@@ -140,6 +141,7 @@ struct fsmc_ctx {
   DevBuf<float> seedGenPos;
   DevBuf<fsmc_match> seedOut;
   DevBuf<uint32_t> seedRank;              // [W][H] seed-map iteration ranks (FSMC_SEED_REFERENCE_ORDER)
+  DevBuf<unsigned char> seedLowComplexity; // [W] low-complexity flags (fsmc_seed_params.skip)
   fsmc::CandidateOrderer orderer;         // device-side reference candidate order (seed_order.h)
   const fsmc_match* orderedOut = nullptr; // its result, valid until the next fsmc_seed call
   bool seedCacheValid = false;  // seedOut holds every interval of the last fsmc_seed call (which overflowed the caller)
@@ -1127,6 +1129,7 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   key.genPosSum = checksum(sp->geneticPositions, sizeof(float) * static_cast<size_t>(L));
   key.globalIdSum = checksum(sp->globalHapId, sizeof(uint32_t) * H);
   key.flipSum = (refOrder && sp->flipMask) ? checksum(sp->flipMask, sizeof(uint64_t) * static_cast<size_t>(std::max(W, 0))) : 0;
+  key.skip = sp->skip;
   key.window[0] = sp->loI;
   key.window[1] = sp->hiI;
   key.window[2] = sp->loJ;
@@ -1225,10 +1228,29 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
     std::vector<uint32_t> hostRank;
     std::thread rankThread;
     double rankMs = 0.0;
-    if (refOrder && W > 0) {
+    const bool useSkip = sp->skip > 0.f;
+    if ((refOrder || useSkip) && W > 0) {
       hostKeys.resize(static_cast<size_t>(W) * H);
       FSMC_CUDA(cudaMemcpyAsync(hostKeys.data(), ctx->seedKeysT.p, hostKeys.size() * sizeof(uint64_t), cudaMemcpyDeviceToHost, st));
       FSMC_CUDA(cudaStreamSynchronize(st));
+    }
+    a.lowComplexity = nullptr;
+    if (useSkip && W > 0) {
+      // ref: FastSMC.cpp:208-219 — float(#distinct words) / float(#haplotypes) > skip, else the word is skipped
+      std::vector<unsigned char> lc(static_cast<size_t>(W), 0);
+      const float skip = sp->skip;
+      candidate_order::parallelForWords(W, 0, [&](const int w) {
+        std::vector<uint64_t> keys(hostKeys.begin() + static_cast<size_t>(w) * H, hostKeys.begin() + static_cast<size_t>(w + 1) * H);
+        std::sort(keys.begin(), keys.end());
+        const size_t distinct = static_cast<size_t>(std::unique(keys.begin(), keys.end()) - keys.begin());
+        lc[w] = !(static_cast<float>(static_cast<int>(distinct)) / static_cast<float>(H) > skip);
+      });
+      FSMC_CUDA(ctx->seedLowComplexity.ensure(static_cast<size_t>(W)));
+      FSMC_CUDA(cudaMemcpyAsync(ctx->seedLowComplexity.p, lc.data(), lc.size(), cudaMemcpyHostToDevice, st));
+      FSMC_CUDA(cudaStreamSynchronize(st));
+      a.lowComplexity = ctx->seedLowComplexity.p;
+    }
+    if (refOrder && W > 0) {
       const uint64_t* flip = sp->flipMask;
       rankThread = std::thread([&hostKeys, &hostRank, &rankMs, flip, H, W] {
         const auto t0 = std::chrono::steady_clock::now();

@@ -53,9 +53,12 @@ void ASMC::FastSMC::seedAndDecode()
   if (mParams.hashingWordSize != 64) {
     throw std::runtime_error("only 64-SNP hashing words are supported");
   }
-  if (mParams.skip != 0.f || mParams.max_seeds != 0 || mParams.min_maf != 0.f || !mParams.haploid) {
-    throw std::runtime_error("the B200 build supports the default seeding options only: skip=0, max_seeds=0, "
-                             "min_maf=0, haploid (gap and min_m are free)");
+  if (mParams.max_seeds != 0 || mParams.min_maf != 0.f || !mParams.haploid) {
+    throw std::runtime_error("the B200 build does not support max_seeds > 0, min_maf > 0 or diploid hashing "
+                             "(gap, min_m and skip are free)");
+  }
+  if (mParams.skip > 0.f && mParams.referenceCandidateOrder && std::getenv("FSMC_HOST_ORDER") != nullptr) {
+    throw std::runtime_error("skip > 0 needs the device candidate order (unset FSMC_HOST_ORDER)");
   }
   const uint32_t H = static_cast<uint32_t>(mData.numLoadedHaplotypes());
   const int W = mData.sites / 64;
@@ -77,6 +80,7 @@ void ASMC::FastSMC::seedAndDecode()
   static const bool hostOrder = std::getenv("FSMC_HOST_ORDER") != nullptr;
   const bool deviceOrder = mParams.referenceCandidateOrder && !hostOrder;
   sp.flipMask = mData.flipMask.data();
+  sp.skip = mParams.skip;
   sp.flags = deviceOrder ? FSMC_SEED_REFERENCE_ORDER
                          : (mParams.referenceCandidateOrder ? (FSMC_SEED_ALL_INTERVALS | FSMC_SEED_UNSORTED) : 0u);
 

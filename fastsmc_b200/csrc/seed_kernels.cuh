@@ -67,6 +67,7 @@ struct SeedArgs {
   unsigned long long* batchChunkBase;  // [wordsInBatch + 1] exclusive scan of the words' chunk counts, then [+1] cursor
   fsmc_match* out;
   long long capacity;
+  const unsigned char* lowComplexity;  // [W] 1 = low-complexity word (DecodingParams::skip), nullptr = none
 };
 
 // The tables of word j of the batch.
@@ -225,6 +226,9 @@ __global__ void batchChunksKernel(const SeedArgs a)
     unsigned long long run = 0;
     for (int j = 0; j < a.wordsInBatch; ++j) {
       a.batchChunkBase[j] = run;
+      if (a.lowComplexity && a.lowComplexity[a.wordBase + j]) {
+        continue;  // no pair is seeded at a low-complexity word (ref: FastSMC.cpp:212-219)
+      }
       run += (a.wordCounters[static_cast<size_t>(j) * 4 + 2] + kPairsPerChunk - 1) / kPairsPerChunk;
     }
     a.batchChunkBase[a.wordsInBatch] = run;
@@ -320,10 +324,18 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
           isStart = true;
           const uint64_t* A = a.haps + static_cast<size_t>(hLo) * a.wordsPerHap;
           const uint64_t* B = a.haps + static_cast<size_t>(hHi) * a.wordsPerHap;
-          for (int d = 1; d <= a.gap + 1 && w - d >= 0; ++d) {
-            if (__ldg(A + w - d) == __ldg(B + w - d)) {
+          // alive before w?  Walk back: gap+1 misses in a row mean the earlier interval was flushed; a low-complexity
+          // word extends whatever is alive without being a match itself, so it restarts the count of misses
+          // (ref: ExtendHash.hpp:85-106)
+          int missesBack = 0;
+          for (int x = w - 1; x >= 0 && missesBack <= a.gap; --x) {
+            if (a.lowComplexity && a.lowComplexity[x]) {
+              missesBack = 0;
+            } else if (__ldg(A + x) == __ldg(B + x)) {
               isStart = false;
               break;
+            } else {
+              ++missesBack;
             }
           }
         }
@@ -348,7 +360,7 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
         const uint64_t* A = a.haps + static_cast<size_t>(hLo) * a.wordsPerHap;
         const uint64_t* B = a.haps + static_cast<size_t>(hHi) * a.wordsPerHap;
         for (int k = 0; k < kLaneWords && open && pos < a.W; ++k, ++pos) {
-          if (__ldg(A + pos) == __ldg(B + pos)) {
+          if ((a.lowComplexity && a.lowComplexity[pos]) || __ldg(A + pos) == __ldg(B + pos)) {
             end = pos;
             misses = 0;
           } else if (++misses > a.gap) {
@@ -371,7 +383,7 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
         bool sOpen = true;
         for (int p0 = sPos; p0 < a.W && sOpen; p0 += 32) {
           const int x = p0 + static_cast<int>(lane);
-          const bool eq = x < a.W && __ldg(A + x) == __ldg(B + x);
+          const bool eq = x < a.W && ((a.lowComplexity && a.lowComplexity[x]) || __ldg(A + x) == __ldg(B + x));
           const unsigned m = __ballot_sync(0xffffffffu, eq);
           const int valid = min(32, a.W - p0);
           for (int b = 0; b < valid; ++b) {  // warp-uniform walk over the 32 comparison bits

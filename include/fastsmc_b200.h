@@ -215,7 +215,9 @@ int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan);
  * their 64-SNP words are identical (the reference's hash is the identity on the word, SURVEY F5;
  * minor-allele folding flips both haplotypes alike, so folded words compare like raw ones).  A
  * match interval [startWord, endWord] of a pair a < b starts at a matching word with no match in
- * the preceding gap+1 words, and is extended while the next match is at most gap+1 words ahead.
+ * the preceding gap+1 words, and is extended while the next match is at most gap+1 words ahead
+ * (low-complexity words, see fsmc_seed_params.skip, count as neither match nor miss for an open interval
+ * and move its end).
  * Intervals are produced for pairs that pass the job filter on GLOBAL haplotype ids
  * (HASHING/SeedHash.hpp:99-129) and, unless FSMC_SEED_ALL_INTERVALS is set, whose genetic length
  * 100*(gen[min(64*end+63, L-1)] - gen[64*start]) is >= minLengthCm.
@@ -251,6 +253,10 @@ typedef struct fsmc_seed_params {
   /* [sites/64] (host) bit s%64 of word s/64 = site s was flipped by folding: raw word = word ^ flipMask[w].
    * NULL = the haplotypes are raw.  Only read with FSMC_SEED_REFERENCE_ORDER.                      */
   const uint64_t* flipMask;
+  /* DecodingParams::skip (FastSMC.cpp:208-219, HASHING/ExtendHash.hpp:102-106): a word whose number of distinct
+   * haplotype words divided by numHaps is <= skip is "low complexity": no pair is seeded at it, and every interval that is
+   * alive there is extended to it.  0 = off (every word has at least one distinct value).                              */
+  float skip;
 } fsmc_seed_params;
 
 typedef struct fsmc_seed_stats {

@@ -363,3 +363,35 @@ def test_device_candidate_order_at_cfg3_density(asmc, oracle_mod, tmp_path):
     assert st.numIntervals > 1_000_000 and st.orderEpochs > 15
     assert len(got) == len(want) > 50_000
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("options", [dict(skip=0.13), dict(skip=0.145, gap=2, min_m=2.5), dict(skip=0.15, gap=0, min_m=1.0)],
+                         ids=["skip0.13", "skip0.145-gap2", "skip0.15-gap0"])
+@pytest.mark.parametrize("reference_order", [True, False], ids=["reference-order", "canonical-order"])
+def test_low_complexity_word_skipping_equals_oracle(asmc, oracle_mod, tmp_path, options, reference_order):
+    """DecodingParams::skip (FastSMC.cpp:208-219, ExtendHash.hpp:102-106): words with few distinct haplotype words seed no
+    pairs and extend every live interval.  Dense synthetic data (6 founders): a quarter to a half of the words are skipped.
+    Candidate stream bit-exact against the oracle (which equals the reference build on this data,
+    tests/test_reference_build.py); in exact mode and reference order the .ibd.gz is identical too."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, 200, 1920, 3000 * 1920, 1, 11, founders=6)
+    options = dict(dict(min_m=2.0), **options)
+    o = oracle_mod.Oracle(root, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, **dict(REGRESSION_PARAMS, **options))
+    want = o.seed().astype(np.int64)
+    p = _synthetic_params(asmc, root, str(tmp_path / "gpu"), FASTSMC_EXAMPLE_DQ, exactArithmetic=True,
+                          referenceCandidateOrder=reference_order, **options)
+    f = asmc.FastSMC(p)
+    f.setKeepCandidates(True)
+    f.run()
+    got = f.getCandidates().astype(np.int64)
+    assert len(want) > 300 and len(got) == len(want)
+    if reference_order:
+        assert np.array_equal(got, want)
+        ref_path = str(tmp_path / "oracle.ibd.gz")
+        n = o.run(ref_path)
+        mine = _lines(f"{p.outFileRoot}.1.1.FastSMC.ibd.gz")
+        assert len(mine) == n and mine == _lines(ref_path)
+    else:
+        key = lambda a: np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))
+        assert np.array_equal(got[key(got)], want[key(want)])  # the same candidate multiset

@@ -46,3 +46,26 @@ def test_reference_default_flags_conditional_age_estimates(oracle_mod, tmp_path)
     path = str(tmp_path / "oracle.ibd.gz")
     o.run(path)
     assert _lines(path) == _lines(f"{out}.1.1.FastSMC.ibd.gz")
+
+
+@pytest.mark.parametrize("options", [dict(skip=0.13), dict(skip=0.145, gap=2, min_m=2.5), dict(max_seeds=20), dict(max_seeds=8, skip=0.13)],
+                         ids=["skip0.13", "skip0.145-gap2", "max_seeds20", "max_seeds8-skip0.13"])
+def test_oracle_equals_reference_build_with_skip_and_max_seeds(oracle_mod, tmp_path, options):
+    """The non-default seeding options (low-complexity word skipping, sub-hashing of oversized buckets; FastSMC.cpp:208-219,
+    HASHING/SeedHash.hpp:56-69, 85-93) on dense synthetic data (6 founders: a quarter to a half of the words are low
+    complexity at these thresholds, buckets of 20-60 haplotypes): reference build vs the oracle, whole .ibd.gz."""
+    if oracle_mod.reference_binary("nosse") is None:
+        pytest.skip("reference build not present")
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, 200, 1920, 3000 * 1920, 1, 11, founders=6)
+    out = str(tmp_path / "ref")
+    options = dict(dict(min_m=2.0), **options)
+    oracle_mod.reference_run("nosse", root, FASTSMC_EXAMPLE_DQ, out, hashing=True, **options)
+    ref = _lines(f"{out}.1.1.FastSMC.ibd.gz")
+    params = dict(REGRESSION_PARAMS, **options)
+    o = oracle_mod.Oracle(root, FASTSMC_EXAMPLE_DQ, str(tmp_path / "orc"), hashing=True, shuffleFlavor=0, **params)
+    path = str(tmp_path / "oracle.ibd.gz")
+    o.run(path)
+    assert len(ref) > 500
+    assert _lines(path) == ref
