@@ -124,6 +124,11 @@ struct fsmc_ctx {
   cudaDeviceProp prop{};
   bool hasModel = false, hasHaps = false;
   fsmc::DeviceModel model{};
+  // The production kernels are specialised for 69 and 159 states.  Any other state count runs on them too: the model is
+  // padded to the next specialised count with states that carry no probability (prior, emissions and transition
+  // coefficients 0: alpha stays 0 there, so every posterior is unchanged).  kernelModel = model when S is 69 or 159.
+  fsmc::DeviceModel kernelModel{};
+  DevBuf<float> kernelSiteRows;
   DevBuf<float> siteRows, prior, expTimes, colRatios;
   DevBuf<uint64_t> haps;
   long long numHaps = 0;
@@ -531,6 +536,21 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
   m.thr[1] = 100 * mdl->probabilityThreshold;
   m.thr[2] = 10 * mdl->probabilityThreshold;
   m.thr[3] = mdl->probabilityThreshold;
+  m.haps = ctx->haps.p;
+  m.wordsPerHap = ctx->hasHaps ? (ctx->sites + 63) / 64 : 0;
+  ctx->kernelModel = m;
+  const int Sk = S <= 69 ? 69 : (S <= 159 ? 159 : 0);
+  if (Sk != 0 && Sk != S) {
+    const int SpadK = (Sk + 3) / 4 * 4;
+    FSMC_CUDA(ctx->kernelSiteRows.ensure(static_cast<size_t>(L) * fsmc::kRowArrays * SpadK));
+    fsmc::buildSiteRowsKernel<<<blocks, threads, 0, st>>>(S, SpadK, L, e1.p, e0.p, e2.p, D.p, B.p, U.p, R.p, rowIdx.p,
+                                                           ctx->kernelSiteRows.p);
+    FSMC_CUDA(cudaGetLastError());
+    FSMC_CUDA(cudaStreamSynchronize(st));
+    ctx->kernelModel.S = Sk;
+    ctx->kernelModel.Spad = SpadK;
+    ctx->kernelModel.siteRows = ctx->kernelSiteRows.p;
+  }
   ctx->hasModel = true;
   return FSMC_OK;
 }
@@ -548,6 +568,8 @@ int fsmc_set_haplotypes(fsmc_ctx* ctx, const uint64_t* bits, const int64_t numHa
   FSMC_CUDA(cudaStreamSynchronize(ctx->stream));
   ctx->model.haps = ctx->haps.p;
   ctx->model.wordsPerHap = words;
+  ctx->kernelModel.haps = ctx->haps.p;
+  ctx->kernelModel.wordsPerHap = words;
   ctx->numHaps = numHaps;
   ctx->sites = sites;
   ctx->hasHaps = true;
@@ -564,9 +586,9 @@ int fsmc_query_kernel(fsmc_ctx* ctx, const uint32_t flags, const double meanScan
     return fail(FSMC_E_STATE, "fsmc_query_kernel: set the model first");
   }
   const DeviceModel& m = ctx->model;
-  const FastChoice fc = chooseFastKernel(m, flags, sparsePreferred(meanScanSites));
+  const FastChoice fc = chooseFastKernel(ctx->kernelModel, flags, sparsePreferred(meanScanSites));
   const KernelChoice kc = chooseKernel(m.S, flags);
-  out->statesKernel = fc.fn ? m.S : kc.statesKernel;
+  out->statesKernel = fc.fn ? ctx->kernelModel.S : kc.statesKernel;
   out->narrowKernel = fc.narrow ? 1 : 0;
   out->sparseKernel = fc.sparse ? 1 : 0;
   out->tileWarps = fc.splitWarps > 0 ? fc.splitWarps : 1;
@@ -711,10 +733,10 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   // (all-pairs decoding, hashing off).  The windows of hashing candidates lie mostly inside runs: dense kernel.
   // FSMC_SPARSE=0/1 overrides the window-length rule (development / tests).
   const bool preferSparse = T > 0 && sparsePreferred(scanSites / static_cast<double>(T));
-  const FastChoice fc = chooseFastKernel(m, flags, preferSparse);
+  const FastChoice fc = chooseFastKernel(ctx->kernelModel, flags, preferSparse);
   plan->fast = fc.fn != nullptr;
   plan->sparse = fc.sparse;
-  plan->statesKernel = plan->fast ? m.S : kc.statesKernel;
+  plan->statesKernel = plan->fast ? ctx->kernelModel.S : kc.statesKernel;
   plan->narrow = fc.narrow;
   plan->tileWarps = fc.splitWarps > 0 ? fc.splitWarps : 1;
   plan->mode = kc.mode;
@@ -724,7 +746,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   int blocksPerSm = 0;
   if (plan->fast) {
     plan->threads = fc.threads;
-    plan->smemBytes = fastSmemBytes(fc, m.S);
+    plan->smemBytes = fastSmemBytes(fc, ctx->kernelModel.S);
     FSMC_CUDA(cudaFuncSetAttribute(fc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
     FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, fc.fn, plan->threads, plan->smemBytes));
   } else {
@@ -861,7 +883,7 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
   }
   FSMC_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
-  const DeviceModel& m = ctx->model;
+  const DeviceModel& m = plan->fast ? ctx->kernelModel : ctx->model;  // the specialised kernels see the padded model
   FSMC_CUDA(cudaEventRecord(ctx->ev[1], st));
   plan->launches = 0;
   if (plan->numTiles > 0) {
@@ -1071,7 +1093,7 @@ int fsmc_plan_collect(fsmc_ctx* ctx, fsmc_plan* plan, const fsmc_decode_request*
     stats->scratchBytes = static_cast<int64_t>(plan->scratchPerWarp) * sizeof(float) * plan->blocks * plan->tilesPerBlock;
     stats->sparseKernel = plan->sparse ? 1 : 0;
     stats->sparseItems = plan->sparse ? plan->itemsFound : 0;
-    stats->checkpointBytes = plan->sparse ? plan->ckptSlots * static_cast<int64_t>(ctx->model.Spad) * 32 * 4 : 0;
+    stats->checkpointBytes = plan->sparse ? plan->ckptSlots * static_cast<int64_t>(ctx->kernelModel.Spad) * 32 * 4 : 0;
     stats->checkpointSites = plan->sparse ? (1 << plan->ckptShift) : 0;
   }
   plan->launched = false;

@@ -552,3 +552,47 @@ def test_cfg2_shape_batches_against_oracle(oracle_mod, tmp_path):
         ratio = sums / prior
         best = int(np.argmax(ratio))
         assert int(s["mapState"]) == best or ratio[int(s["mapState"])] >= ratio[best] * (1 - 1e-3)
+
+
+# ---- state counts other than 69 / 159: padded onto the specialised kernels -----------------------------------------------
+
+
+@pytest.mark.parametrize("source,states,kernel_states", [("synthetic69", 40, 69), ("example", 100, 159), ("synthetic69", 68, 69)])
+def test_other_state_counts_run_on_the_specialised_kernels(request, oracle_mod, source, states, kernel_states):
+    """A decoding-quantities table with any number of states must not fall to the scalar-load kernel: the model is padded
+    with probability-free states to 69 or 159.  Truncating a real table to its first `states` states gives a model with
+    another state count (the recurrences do not care that it is no longer a proper transition matrix); the padded
+    production kernels must agree with the any-S kernel (FSMC_GENERIC_KERNEL, itself checked against the oracle at 69 and
+    159 states) within 1e-4: per-site outputs, segments with all-state and with conditional age estimates."""
+    from conftest import model_from_oracle
+    from fastsmc_b200 import _native as N
+    o, _ = request.getfixturevalue(source)
+    full = model_from_oracle(o, oracle_mod)
+    cut = {k: (v[..., :states].copy() if isinstance(v, np.ndarray) and v.ndim >= 1 and v.shape[-1] == o.states else v)
+           for k, v in full.items()}
+    rng = np.random.default_rng(9)
+    a, b = _pairs(rng, 75, o.num_haps)
+    for age_threshold in (states, full["state_threshold"]):
+        ctx = N.Context(0)
+        ctx.set_model(**dict(cut, age_threshold=age_threshold))
+        ctx.set_haplotypes(N.pack_haplotypes(o.haplotypes()), o.sites)
+        nb = (len(a) + 31) // 32
+        tiles = ctx.make_tiles(a, b, windows=[[3, min(o.sites, 2500)]] * nb, sites=o.sites)
+        if age_threshold == states:
+            fast = ctx.decode(tiles, N.SITE_MEAN | N.SITE_MAP | N.SITE_IBD)
+            slow = ctx.decode(tiles, N.SITE_MEAN | N.SITE_MAP | N.SITE_IBD | N.GENERIC_KERNEL)
+            assert fast.stats.statesKernel == kernel_states and slow.stats.statesKernel == 0
+            rows, n = tiles["rows"], min(o.sites, 2500) - 3
+            np.testing.assert_allclose(fast.site_mean[rows, :n], slow.site_mean[rows, :n], rtol=REL_TOL)
+            np.testing.assert_allclose(fast.site_ibd[rows, :n], slow.site_ibd[rows, :n], rtol=REL_TOL, atol=1e-12)
+            assert (fast.site_map[rows, :n] != slow.site_map[rows, :n]).mean() < 2e-3
+        fast = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE, segment_capacity=1 << 16)
+        slow = ctx.decode(tiles, N.CALL_SEGMENTS | N.SEG_AGE | N.GENERIC_KERNEL, segment_capacity=1 << 16)
+        assert fast.stats.statesKernel == kernel_states and slow.stats.statesKernel == 0
+        gf, gs = {_seg_key(s): s for s in fast.segments}, {_seg_key(s): s for s in slow.segments}
+        both = sorted(set(gf) & set(gs))
+        assert len(both) >= 0.98 * max(len(gf), len(gs)) and len(both) > 5
+        for f in ("prob", "postMean"):
+            np.testing.assert_allclose([gf[k][f] for k in both], [gs[k][f] for k in both], rtol=REL_TOL)
+        assert np.mean([gf[k]["mapState"] != gs[k]["mapState"] for k in both]) < 2e-2
+        ctx.close()
