@@ -135,6 +135,7 @@ struct fsmc_ctx {
   DevBuf<float> scratch, accScratch;
   DevBuf<float> stageE1, stageE0, stageE2, stageD, stageB, stageU, stageR;  // fsmc_set_model staging
   DevBuf<int> stageRowIdx;
+  DevBuf<float> sumScratch;  // decodeFastKernel<SUM>: [resident warp][planes][L][Spad]
   DevBuf<float> ckptBeta;  // sparse age estimates: beta checkpoints of every tile of the current plan (decode_sparse.cuh)
   std::vector<float> hostPrior, hostExpTimes, hostColRatios;
   long long sites = 0;
@@ -189,6 +190,7 @@ struct fsmc_plan {
   bool narrow = false;
   int tileWarps = 1;
   int tilesPerBlock = 1;  // tiles in flight per CTA (= scratch slabs per CTA)
+  bool sumOnFast = false;  // posterior sums through per-warp accumulators (decodeFastKernel<SUM>)
   // sparse age estimates (decode_sparse.cuh)
   bool sparse = false;
   int ckptShift = 5;
@@ -252,6 +254,7 @@ struct FastChoice {
   int splitWarps = 0;       // > 0: decodeSplitKernel, one tile per CTA of this many warps (decode_split.cuh)
   size_t splitSmem = 0;
   bool sparse = false;      // decodeNarrowKernel<SPARSE> + refineKernel (decode_sparse.cuh)
+  bool sum = false;         // decodeFastKernel<SUM>: per-warp accumulators of the posterior sums
 };
 
 // FSMC_SPLIT=0 forces the one-warp-per-tile kernels, FSMC_SPLIT=1 the state-split kernels wherever one exists
@@ -267,8 +270,16 @@ int splitPreference()
 FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bool preferSparse = false)
 {
   const int S = m.S;
-  // full posteriors and their sums are produced by decodeTilesKernel only
-  if ((flags & (FSMC_EXACT | FSMC_GENERIC_KERNEL | FSMC_SITE_POSTERIOR | FSMC_SUM_POSTERIOR)) || S > fsmc::kMaxParamStates) {
+  // full posterior matrices are produced by decodeTilesKernel only; sums over pairs also by decodeFastKernel<69, SUM>
+  if ((flags & (FSMC_EXACT | FSMC_GENERIC_KERNEL | FSMC_SITE_POSTERIOR)) || S > fsmc::kMaxParamStates) {
+    return {};
+  }
+  if (flags & FSMC_SUM_POSTERIOR) {
+    if (S == 69 && !(flags & FSMC_CALL_SEGMENTS)) {
+      FastChoice fc{fsmc::decodeFastKernel<69, kFastDepth, kFastRescale, false, 128, 2, true>, 72, 128, false};
+      fc.sum = true;
+      return fc;
+    }
     return {};
   }
   const bool acc = (flags & FSMC_SEG_AGE) && (flags & FSMC_CALL_SEGMENTS);
@@ -771,6 +782,13 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   blocks = std::min<long long>(blocks, (T + warpsPerBlock - 1) / warpsPerBlock);
   blocks = std::max<long long>(blocks, 1);
 
+  plan->sumOnFast = fc.sum;
+  if (fc.sum) {
+    // private accumulators of the posterior sums, one per resident warp (allocated before the slabs are sized)
+    const size_t perWarp = sumPosteriorCount(m, flags) / static_cast<size_t>(m.S) * static_cast<size_t>(fc.Spad);
+    FSMC_CUDA(ctx->sumScratch.ensure(static_cast<size_t>(blocks) * warpsPerBlock * perWarp));
+  }
+
   // backward-sweep scratch: one slab of maxLen*S*32 floats per resident warp.  Shrink the grid if
   // the slabs would not fit in 85% of the free memory.
   plan->scratchPerWarp = maxLen * (plan->fast ? (fc.narrow ? fc.recordQuads * 4 : fc.Spad) : m.S) * 32;
@@ -924,8 +942,14 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
     a.siteIbd = plan->siteIbd.p;
     a.sitePosterior = plan->sitePosterior.p;
     a.sumPosterior = plan->sumPosterior.p;
+    const int sumPlanes = (plan->flags & FSMC_SUM_BY_GENOTYPE) ? 3 : 1;
+    const int sumWarps = plan->blocks * plan->tilesPerBlock;
     if (plan->flags & FSMC_SUM_POSTERIOR) {
-      FSMC_CUDA(cudaMemsetAsync(plan->sumPosterior.p, 0, sumPosteriorCount(m, plan->flags) * sizeof(float), st));
+      FSMC_CUDA(cudaMemsetAsync(plan->sumPosterior.p, 0, sumPosteriorCount(ctx->model, plan->flags) * sizeof(float), st));
+      if (plan->sumOnFast) {
+        a.sumScratch = ctx->sumScratch.p;
+        FSMC_CUDA(cudaMemsetAsync(ctx->sumScratch.p, 0, static_cast<size_t>(sumWarps) * sumPlanes * m.L * m.Spad * sizeof(float), st));
+      }
     }
     a.siteStride = plan->siteStride;
     a.scratch = ctx->scratch.p;
@@ -940,6 +964,11 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
       std::copy(ctx->hostPrior.begin(), ctx->hostPrior.end(), fm.prior);
       const FastChoice fc = chooseFastKernel(m, plan->flags, plan->sparse);
       fc.fn<<<plan->blocks, plan->threads, plan->smemBytes, st>>>(fm, a);
+      if (plan->sumOnFast) {
+        fsmc::sumScratchReduceKernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(ctx->sumScratch.p, sumWarps, sumPlanes, m.L,
+                                                                                        ctx->model.S, m.Spad, plan->sumPosterior.p);
+        plan->launches += 1;
+      }
       if (plan->sparse) {
         // items by block, full posteriors inside the items, age estimates of the segments
         const long long cap = plan->itemCapacity;

@@ -768,7 +768,12 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
 // S_T   : states (compile time), DEPTH: ring depth, RESCALE: sites between rescalings (power of two)
 // ACC   : keep per-state segment accumulators (FSMC_SEG_AGE) in registers
 // -------------------------------------------------------------------------------------------------------------------
-template <int S_T, int DEPTH, int RESCALE, bool ACC, int THREADS, int MIN_BLOCKS>
+// SUM   : FSMC_SUM_POSTERIOR[_BY_GENOTYPE] (ref: HMM.cpp:1044-1085 augmentSumOverPairs).  Every resident warp adds the
+//         posteriors of its tiles into a PRIVATE [plane][site][state] accumulator in global memory (plain read-add-write,
+//         no atomics; the 32 pairs of a tile are first added up through the drained beta slot in shared memory), tiles are
+//         dealt to the warps statically, and sumScratchReduceKernel adds the warps' accumulators in a fixed order: the
+//         result does not depend on scheduling.
+template <int S_T, int DEPTH, int RESCALE, bool ACC, int THREADS, int MIN_BLOCKS, bool SUM = false>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const FastModel fm, const DecodeArgs args)
 {
   constexpr int S = S_T;
@@ -808,13 +813,20 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
   const int nAcc = m.ageThreshold;
   const long long warpGlobal = static_cast<long long>(blockIdx.x) * kWarps + warp;
   float* slab = args.scratch + warpGlobal * args.scratchPerWarp;  // beta rows of this warp
+  const int sumPlanes = SUM && (flags & FSMC_SUM_BY_GENOTYPE) ? 3 : 1;
+  float* sumMine = SUM ? args.sumScratch + static_cast<size_t>(warpGlobal) * sumPlanes * m.L * Spad : nullptr;
+  const long long totalWarps = static_cast<long long>(gridDim.x) * kWarps;
 
-  for (;;) {
+  for (long long turn = 0;; ++turn) {
     unsigned long long t = 0;
-    if (lane == 0) {
-      t = atomicAdd(args.tileCounter, 1ull);
+    if constexpr (SUM) {
+      t = static_cast<unsigned long long>(warpGlobal + turn * totalWarps);  // static deal: reproducible sums
+    } else {
+      if (lane == 0) {
+        t = atomicAdd(args.tileCounter, 1ull);
+      }
+      t = __shfl_sync(kFull, t, 0);
     }
-    t = __shfl_sync(kFull, t, 0);
     if (static_cast<long long>(t) >= args.numTiles) {
       break;
     }
@@ -975,6 +987,48 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
           }
         }
 
+        if constexpr (SUM) {
+          // posteriors of the tile's 32 pairs -> [state][pair] in the drained beta slot, then lane l adds up states
+          // l, l+32, l+64 (reading the pairs rotated by its lane number: conflict-free) and updates the warp's accumulator
+          float* stage = reinterpret_cast<float*>(betaSlot(slot));
+          const int cls = bits.cls(site);
+          const unsigned het = __ballot_sync(kFull, cls == 1), minor = __ballot_sync(kFull, cls == 2);
+          const float rr = laneActive ? r : 0.f;
+          __syncwarp();  // every lane has read its beta quads
+#pragma unroll
+          for (int k = 0; k < S; ++k) {
+            stage[k * 32 + lane] = w[k] * rr;
+          }
+          __syncwarp();
+          const bool byGenotype = sumPlanes == 3;
+#pragma unroll
+          for (int j = 0; j < (S + 31) / 32; ++j) {
+            const int k = lane + 32 * j;
+            if (k < S) {
+              float s0 = 0.f, s1 = 0.f, s2 = 0.f;
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                const int src = (i + lane) & 31;
+                const float v = stage[k * 32 + src];
+                if (byGenotype) {
+                  const bool h = (het >> src) & 1u, mn = (minor >> src) & 1u;
+                  s0 += (h || mn) ? 0.f : v;
+                  s1 += h ? v : 0.f;
+                  s2 += mn ? v : 0.f;
+                } else {
+                  s0 += v;
+                }
+              }
+              float* row = sumMine + static_cast<size_t>(site) * Spad + k;
+              row[0] += s0;
+              if (byGenotype) {
+                row[static_cast<size_t>(m.L) * Spad] += s1;
+                row[2 * static_cast<size_t>(m.L) * Spad] += s2;
+              }
+            }
+          }
+        }
+
         const bool inScan = wantSeg && site >= scanFrom && site < scanTo;
         if ((flags & FSMC_SITE_IBD) || inScan) {
           forStatesBelow<S_T>(sT, [&](const int k) { ibdRaw += w[k]; });
@@ -1099,6 +1153,27 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeFastKernel(const Fa
       }
     }
     __syncwarp();
+  }
+}
+
+// out[(plane * S + k) * L + site] = sum over warps of scratch[warp][plane][site][k], warps in ascending order
+static __global__ void sumScratchReduceKernel(const float* __restrict__ scratch, const int warps, const int planes, const int L,
+                                              const int S, const int Spad, float* __restrict__ out)
+{
+  const long long total = static_cast<long long>(planes) * L * Spad;
+  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < total;
+       i += static_cast<long long>(gridDim.x) * blockDim.x) {
+    const int k = static_cast<int>(i % Spad);
+    if (k >= S) {
+      continue;
+    }
+    const long long site = (i / Spad) % L;
+    const long long plane = i / Spad / L;
+    float sum = 0.f;
+    for (int w = 0; w < warps; ++w) {
+      sum += scratch[static_cast<size_t>(w) * total + i];
+    }
+    out[(plane * S + k) * L + site] = sum;
   }
 }
 

@@ -91,6 +91,8 @@ struct DecodeArgs {
   long long itemCapacity;
   const uint32_t* itemOrder;        // items sorted by block (refine pass)
   unsigned long long* refineCounter;
+  // ---- sums of posteriors over pairs on the production kernel: private accumulators per resident warp ------------------
+  float* sumScratch;                // [warp][planes][L][Spad]
 };
 
 // ---- arithmetic: EXACT = separate IEEE multiply and add (never contracted), else FMA ------------

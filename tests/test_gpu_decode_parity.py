@@ -596,3 +596,24 @@ def test_other_state_counts_run_on_the_specialised_kernels(request, oracle_mod, 
             np.testing.assert_allclose([gf[k][f] for k in both], [gs[k][f] for k in both], rtol=REL_TOL)
         assert np.mean([gf[k]["mapState"] != gs[k]["mapState"] for k in both]) < 2e-2
         ctx.close()
+
+
+def test_posterior_sums_on_the_production_kernel(synthetic69):
+    """FSMC_SUM_POSTERIOR[_BY_GENOTYPE] (ref: HMM.cpp:1044-1085): decodeFastKernel<69, SUM> (per-warp accumulators, static
+    tile deal, ordered reduction) vs the any-S kernel's float atomics: same sums to rounding, and bit-identical from run
+    to run."""
+    from fastsmc_b200 import _native as N
+    o, ctx = synthetic69
+    rng = np.random.default_rng(17)
+    a, b = _pairs(rng, 32 * 50 + 9, o.num_haps)
+    tiles = ctx.make_tiles(a, b, sites=o.sites)
+    for extra in (0, N.SUM_BY_GENOTYPE):
+        fast = ctx.decode(tiles, N.SUM_POSTERIOR | extra)
+        again = ctx.decode(tiles, N.SUM_POSTERIOR | extra)
+        slow = ctx.decode(tiles, N.SUM_POSTERIOR | extra | N.GENERIC_KERNEL)
+        assert fast.stats.statesKernel == 69 and slow.stats.statesKernel == 0
+        assert fast.sum_posterior.shape == ((3 if extra else 1), o.states, o.sites)
+        assert fast.sum_posterior.tobytes() == again.sum_posterior.tobytes()
+        np.testing.assert_allclose(fast.sum_posterior, slow.sum_posterior, rtol=2e-4, atol=1e-6)
+        # every pair contributes a distribution over the states at every site
+        np.testing.assert_allclose(fast.sum_posterior.sum(axis=(0, 1)), len(a), rtol=1e-4)
