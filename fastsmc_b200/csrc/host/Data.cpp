@@ -1,6 +1,8 @@
 // fastsmc_b200 host layer — see Data.hpp.
 #include "Data.hpp"
 
+#include <sys/stat.h>
+
 #include <algorithm>
 #include <cstring>
 #include <thread>
@@ -118,7 +120,168 @@ bool Data::readSample(const unsigned n) const
          (jobs == jobInd && n >= ((w_j - 1) * windowSize) / 2);
 }
 
+namespace
+{
+constexpr char kCacheMagic[8] = {'F', 'S', 'M', 'C', 'B', 'I', 'T', '2'};
+
+// what the cache depends on: the three input files (size and modification time) and the options that shape the matrix
+struct CacheKey {
+  long long size[3], mtime[3];
+  int fold, csfs;
+};
+bool cacheKeyOf(const DecodingParams& params, CacheKey& key)
+{
+  const std::string files[3] = {hapsFile(params.inFileRoot), samplesFile(params.inFileRoot),
+                                FileUtils::firstExisting(params.inFileRoot, {".map.gz", ".map"})};
+  for (int i = 0; i < 3; ++i) {
+    struct stat st;
+    if (stat(files[i].c_str(), &st) != 0) {
+      return false;
+    }
+    key.size[i] = static_cast<long long>(st.st_size);
+    key.mtime[i] = static_cast<long long>(st.st_mtime);
+  }
+  key.fold = params.foldData;
+  key.csfs = params.usingCSFS;
+  return true;
+}
+template <class T> void writeVec(std::FILE* f, const std::vector<T>& v)
+{
+  const uint64_t n = v.size();
+  std::fwrite(&n, sizeof n, 1, f);
+  if (n) {
+    std::fwrite(v.data(), sizeof(T), n, f);
+  }
+}
+template <class T> bool readVec(std::FILE* f, std::vector<T>& v)
+{
+  uint64_t n = 0;
+  if (std::fread(&n, sizeof n, 1, f) != 1 || n > (uint64_t{1} << 40)) {
+    return false;
+  }
+  v.resize(n);
+  return n == 0 || std::fread(v.data(), sizeof(T), n, f) == n;
+}
+bool cacheWanted(const DecodingParams& params)
+{
+  const char* e = std::getenv("FSMC_HAP_CACHE");
+  return params.FastSMC && (params.hapBitCache || (e && *e && *e != '0'));
+}
+}  // namespace
+
+std::string Data::bitCachePath(const std::string& inFileRoot)
+{
+  return hapsFile(inFileRoot) + ".fsmcbits";
+}
+
+void Data::writeBitCache(const DecodingParams& params) const
+{
+  CacheKey key{};
+  if (!cacheKeyOf(params, key) || numLoadedHaplotypes() != haploidSampleSize) {
+    return;
+  }
+  const std::string path = bitCachePath(params.inFileRoot), tmp = path + ".tmp";
+  std::FILE* f = std::fopen(tmp.c_str(), "wb");
+  if (!f) {
+    return;  // read-only data directory: no cache, no error
+  }
+  std::fwrite(kCacheMagic, 1, sizeof kCacheMagic, f);
+  std::fwrite(&key, sizeof key, 1, f);
+  const long long header[4] = {static_cast<long long>(sampleSize), sites, chrNumber, wordsPerHap};
+  std::fwrite(header, sizeof header, 1, f);
+  writeVec(f, hapBits);
+  writeVec(f, flipMask);
+  writeVec(f, totalSamplesCount);
+  writeVec(f, derivedAlleleCounts);
+  writeVec(f, physicalPositions);
+  writeVec(f, geneticPositions);
+  writeVec(f, recRateAtMarker);
+  const bool ok = std::fflush(f) == 0 && !std::ferror(f);
+  std::fclose(f);
+  if (ok) {
+    std::rename(tmp.c_str(), path.c_str());
+  } else {
+    std::remove(tmp.c_str());
+  }
+}
+
+bool Data::loadBitCache(const DecodingParams& params, Data& whole)
+{
+  CacheKey want{}, have{};
+  if (!cacheKeyOf(params, want)) {
+    return false;
+  }
+  std::FILE* f = std::fopen(bitCachePath(params.inFileRoot).c_str(), "rb");
+  if (!f) {
+    return false;
+  }
+  struct Closer {
+    std::FILE* f;
+    ~Closer() { std::fclose(f); }
+  } closer{f};
+  char magic[sizeof kCacheMagic];
+  long long header[4];
+  if (std::fread(magic, 1, sizeof magic, f) != sizeof magic || std::memcmp(magic, kCacheMagic, sizeof magic) != 0 ||
+      std::fread(&have, sizeof have, 1, f) != 1 || std::memcmp(&have, &want, sizeof want) != 0 ||
+      std::fread(header, sizeof header, 1, f) != 1) {
+    return false;  // another format, or the input files / options changed since it was written
+  }
+  Data d;
+  d.sampleSize = static_cast<unsigned long>(header[0]);
+  d.haploidSampleSize = 2ul * d.sampleSize;
+  d.sites = static_cast<int>(header[1]);
+  d.chrNumber = static_cast<int>(header[2]);
+  d.wordsPerHap = static_cast<long>(header[3]);
+  DecodingParams wholeParams = params;
+  wholeParams.jobs = 1;
+  wholeParams.jobInd = 1;
+  d.setJobGeometry(wholeParams);
+  if (!readVec(f, d.hapBits) || !readVec(f, d.flipMask) || !readVec(f, d.totalSamplesCount) || !readVec(f, d.derivedAlleleCounts) ||
+      !readVec(f, d.physicalPositions) || !readVec(f, d.geneticPositions) || !readVec(f, d.recRateAtMarker) ||
+      d.hapBits.size() != d.haploidSampleSize * static_cast<size_t>(d.wordsPerHap) || static_cast<int>(d.geneticPositions.size()) != d.sites) {
+    return false;
+  }
+  d.siteWasFlippedDuringFolding.resize(static_cast<size_t>(d.sites));
+  for (int s = 0; s < d.sites; ++s) {
+    d.siteWasFlippedDuringFolding[static_cast<size_t>(s)] = (d.flipMask[static_cast<size_t>(s) >> 6] >> (s & 63)) & 1ull;
+  }
+  d.readSamplesList(params.inFileRoot);  // ids of every sample (jobs = 1)
+  if (d.famAndIndNameList.size() != d.sampleSize) {
+    return false;
+  }
+  d.globalHapId.resize(d.haploidSampleSize);
+  for (size_t h = 0; h < d.globalHapId.size(); ++h) {
+    d.globalHapId[h] = static_cast<uint32_t>(h);
+  }
+  whole = std::move(d);
+  return true;
+}
+
 Data::Data(const DecodingParams& params)
+{
+  if (cacheWanted(params)) {
+    // the packed matrix of the whole data set, from the cache or read once and cached; a job is cut out of it
+    Data whole;
+    if (!loadBitCache(params, whole)) {
+      DecodingParams wholeParams = params;
+      wholeParams.jobs = 1;
+      wholeParams.jobInd = 1;
+      whole.readFromFiles(wholeParams);
+      whole.writeBitCache(params);
+    } else {
+      std::cout << "Read data for " << whole.haploidSampleSize << " haploid samples from " << bitCachePath(params.inFileRoot) << std::endl;
+    }
+    const bool jobbing = params.jobInd != -1 && params.jobs != -1 && params.jobs > 1;
+    *this = jobbing ? forJob(whole, params) : std::move(whole);
+    if (!jobbing) {
+      setJobGeometry(params);
+    }
+    return;
+  }
+  readFromFiles(params);
+}
+
+void Data::readFromFiles(const DecodingParams& params)
 {
   const std::string& root = params.inFileRoot;
   // `sites` is set by the reader itself (finishSites): counting the lines first would inflate the whole .hap.gz one

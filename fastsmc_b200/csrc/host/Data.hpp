@@ -78,6 +78,12 @@ public:
   /// with jobs = jobInd = 1): the same object Data(params) would read from the files, without reading them again.
   static Data forJob(const Data& whole, const DecodingParams& params);
 
+  /// Packed-matrix cache of a FastSMC-mode data set read with jobs = 1 (DecodingParams::hapBitCache): false when there is
+  /// no valid cache for these files and options.
+  static bool loadBitCache(const DecodingParams& params, Data& whole);
+  void writeBitCache(const DecodingParams& params) const;
+  static std::string bitCachePath(const std::string& inFileRoot);
+
   static int countHapLines(std::string inFileRoot);
   static int countSamplesLines(std::string inFileRoot);
 
@@ -96,6 +102,7 @@ public:
   bool readSample(unsigned linesProcessed) const;
 
 private:
+  void readFromFiles(const DecodingParams& params);
   void setJobGeometry(const DecodingParams& params);
   void readSamplesList(const std::string& inFileRoot);
   void readHapsFastSMC(const std::string& inFileRoot, const std::vector<std::pair<unsigned long, double>>& geneticMap);

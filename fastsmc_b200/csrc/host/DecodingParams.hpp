@@ -66,6 +66,11 @@ public:
   // order (needed for record-for-record identical output).  false = canonical order
   // (flush word, then pair key), which is cheaper at scale.
   bool referenceCandidateOrder = true;
+  /// Input codec: keep the packed haplotype matrix of the whole data set next to the haps file
+  /// (<haps file>.fsmcbits) and load that instead of inflating and parsing the text again, as long as the .samples /
+  /// .map / haps files have not changed.  Written by the first FastSMC-mode read that has it switched on; also switched
+  /// on by the environment variable FSMC_HAP_CACHE=1.
+  bool hapBitCache = false;
   // B200 build only: the IBD file is written as concatenated gzip members compressed on `outputThreads` host
   // threads (0 = all cores) at this zlib level; gunzip yields the reference's byte stream at any level.
   int outputCompressionLevel = 1;

@@ -212,6 +212,7 @@ PYBIND11_MODULE(pyASMC, m)
       .def_readwrite("device", &DecodingParams::device)
       .def_readwrite("exactArithmetic", &DecodingParams::exactArithmetic)
       .def_readwrite("referenceCandidateOrder", &DecodingParams::referenceCandidateOrder)
+      .def_readwrite("hapBitCache", &DecodingParams::hapBitCache)
       .def_readwrite("outputCompressionLevel", &DecodingParams::outputCompressionLevel)
       .def_readwrite("outputThreads", &DecodingParams::outputThreads)
       .def_readwrite("verbose", &DecodingParams::verbose);
@@ -279,6 +280,9 @@ PYBIND11_MODULE(pyASMC, m)
       .def_readwrite("w_j", &Data::w_j)
       .def_readwrite("is_j_above_diag", &Data::is_j_above_diag)
       .def_readwrite("globalHapId", &Data::globalHapId)
+      .def_readonly("flipMask", &Data::flipMask)
+      .def_readonly("totalSamplesCount", &Data::totalSamplesCount)
+      .def_readonly("derivedAlleleCounts", &Data::derivedAlleleCounts)
       .def_readwrite("wordsPerHap", &Data::wordsPerHap)
       .def_property_readonly("hapBits",
                              [](const Data& d) {

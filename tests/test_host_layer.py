@@ -214,3 +214,54 @@ def test_job_data_cut_from_one_read_equals_reading_the_job(asmc):
             assert a.sites == b.sites and list(a.physicalPositions) == list(b.physicalPositions)
             assert np.array_equal(np.array(a.geneticPositions), np.array(b.geneticPositions))
             assert a.calculateUndistinguishedCounts(50) == b.calculateUndistinguishedCounts(50)
+
+
+def test_packed_matrix_cache_equals_text_read(asmc, tmp_path):
+    """Input codec: with hapBitCache the packed matrix of the whole data set is written next to the haps file
+    on the first read and loaded instead of the gz text afterwards — for the whole data set and for every job cut out of
+    it — and a cache whose source files changed is ignored."""
+    import shutil
+    import time
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "syn")
+    synth.dataset(root, 120, 1500, 4_500_000, 1, 5)
+
+    def params(cache, jobs=1, job_ind=1):
+        p = asmc.DecodingParams()
+        p.verbose = False
+        p.inFileRoot, p.decodingQuantFile, p.outFileRoot = root, DQ_69, root + ".out"
+        p.decodingModeString, p.foldData, p.usingCSFS, p.FastSMC, p.hashing = "array", True, True, True, True
+        p.jobs, p.jobInd, p.hapBitCache = jobs, job_ind, cache
+        p.validateParamsFastSMC()
+        return p
+
+    def same(x, y):
+        assert x.sites == y.sites and list(x.IIDList) == list(y.IIDList) and x.chrNumber == y.chrNumber
+        for f in ("hapBits", "flipMask", "globalHapId", "totalSamplesCount", "derivedAlleleCounts", "geneticPositions",
+                  "physicalPositions"):
+            assert np.array_equal(np.array(getattr(x, f)), np.array(getattr(y, f))), f
+        assert (x.windowSize, x.w_i, x.w_j, x.is_j_above_diag) == (y.windowSize, y.w_i, y.w_j, y.is_j_above_diag)
+
+    cache = root + ".hap.gz.fsmcbits"
+    plain = asmc.Data(params(False))
+    assert not os.path.exists(cache)
+    first = asmc.Data(params(True))       # reads the text, writes the cache
+    assert os.path.exists(cache)
+    second = asmc.Data(params(True))      # reads the cache
+    same(plain, first)
+    same(plain, second)
+    for jobs, job_ind in ((4, 1), (4, 3), (4, 4), (9, 5)):
+        same(asmc.Data(params(False, jobs, job_ind)), asmc.Data(params(True, jobs, job_ind)))
+    # a changed haps file invalidates the cache: flip one allele of the first site and rewrite
+    import gzip
+    lines = gzip.open(root + ".hap.gz", "rt").read().splitlines()
+    t = lines[0].split(" ")
+    t[5] = "1" if t[5] == "0" else "0"
+    lines[0] = " ".join(t)
+    time.sleep(1.1)  # modification times have one-second resolution
+    with gzip.open(root + ".hap.gz", "wt") as f:
+        f.write("\n".join(lines) + "\n")
+    changed_plain = asmc.Data(params(False))
+    changed_cached = asmc.Data(params(True))
+    same(changed_plain, changed_cached)
+    assert not np.array_equal(np.array(changed_plain.hapBits), np.array(plain.hapBits))
