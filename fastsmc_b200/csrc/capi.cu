@@ -312,13 +312,7 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bo
                                 : fsmc::decodeNarrowKernel<69, 4, 2, kFastDepth, 128, 2, 1>;
     if (const char* e = std::getenv("FSMC_SPARSE_VARIANT")) {  // timing experiments (results are wrong)
       const int v = std::atoi(e);
-      if (rq == 1 && v == 3) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 3>;
-      if (rq == 1 && v == 5) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 5>;
-      if (rq == 1 && v == 7) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 7>;
-      if (rq == 1 && v == 9) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 9>;
-      if (rq == 1 && v == 17) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 17>;
-      if (rq == 1 && v == 33) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 33>;
-      if (rq == 1 && v == 57) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 57>;
+      if (rq == 1 && v == 65) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 65>;  // groups not unrolled
     }
     FastChoice fc{fn, 72, 128, false, true, rq};
     fc.sparse = true;
@@ -819,9 +813,9 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     size_t freeB = 0, totalB = 0;
     FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
     const double budget = 0.45 * static_cast<double>(freeB + ctx->ckptBeta.n * sizeof(float));
-    // blocks of 128 sites (measured on cfg2: 401 / 378 / 364 / 359 ms per step with blocks of 32 / 64 / 128 / 256 sites:
-    // every block boundary inside an IBD run costs the warp an item, and every block a checkpoint); coarser when the
-    // checkpoints of the whole request would not fit
+    // blocks of 128 sites (measured on cfg2: 385 ms per step with blocks of 32 sites, 340 ms with 128: every block boundary
+    // inside an IBD run costs the warp an item, and every block a checkpoint); coarser when the checkpoints of the whole
+    // request would not fit
     int shift = 7;
     if (const char* e = std::getenv("FSMC_CKPT_SHIFT")) {
       shift = std::max(2, std::min(10, std::atoi(e)));
@@ -831,7 +825,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
       long long slots = 0;
       for (long long t = 0; t < T; ++t) {
         base[t] = slots;
-        slots += ((req->tileTo[t] - 1) >> shift) - (req->tileFrom[t] >> shift) + 1;
+        slots += ((req->tileTo[t] - req->tileFrom[t] - 1) >> shift) + 1;  // blocks count from the window's first site
       }
       base[T] = slots;
       if (static_cast<double>(slots) * vecFloats * sizeof(float) <= budget || shift >= 12) {
@@ -977,13 +971,13 @@ int fsmc_plan_launch(fsmc_ctx* ctx, fsmc_plan* plan)
         uint32_t* index = keys + 2 * cap;
         uint32_t* indexOut = keys + 3 * cap;
         const int kb = static_cast<int>(std::min<long long>((cap + 255) / 256, ctx->prop.multiProcessorCount * 8ll));
-        fsmc::itemKeysKernel<<<kb, 256, 0, st>>>(a.items, a.itemCount, cap, keys, index);
+        fsmc::itemKeysKernel<<<kb, 256, 0, st>>>(a.items, a.itemCount, cap, a.tileFrom, plan->ckptShift, keys, index);
         size_t bytes = plan->sortTempBytes;
         FSMC_CUDA(cub::DeviceRadixSort::SortPairs(plan->sortTemp.p, bytes, keys, keysOut, index, indexOut, static_cast<int>(cap), 0, 32, st));
         DecodeArgs r = a;
         r.scratchPerWarp = (1ll << plan->ckptShift) * m.Spad * 32;
         fsmc::refineKernel<69, fsmc::kRefineDepth, kFastRescale, 128, 2><<<plan->refineBlocks, 128, plan->refineSmem, st>>>(fm, r);
-        fsmc::finalizeSegmentsKernel<<<ctx->prop.multiProcessorCount * 4, 256, 0, st>>>(m, a.segments, a.segmentCount, a.segmentCapacity,
+        fsmc::finalizeSegmentsKernel<<<ctx->prop.multiProcessorCount * 8, 256, 0, st>>>(m, a.segments, a.segmentCount, a.segmentCapacity,
                                                                                           a.items, a.itemSums, a.itemCount, cap);
         plan->launches += 4;
       }

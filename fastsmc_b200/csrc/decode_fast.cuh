@@ -340,17 +340,19 @@ template <int S_T, int RQ, int G> struct NarrowSlot {
 // the record (RQ shared-memory accesses) and the segment caller.  Rescaling happens at the last step of every full
 // group, i.e. every G-th site.
 //
-// SPARSE (decode_sparse.cuh): age estimates over ALL states without a beta round trip.  The kernel additionally leaves
-// a full beta vector at the last site of every block of 2^ckptShift sites (checkpoints, 8*S/2^ckptShift bytes per
-// pair-site), keeps alpha of the current block's first site in a per-warp scratch that stays in L2, and records every
-// piece of an IBD run (one item per run and block) together with that alpha.  The refine pass recomputes the full
-// posterior only inside those pieces.
+// SPARSE (decode_sparse.cuh): age estimates over ALL states without a beta round trip.  The window is cut into blocks of
+// 2^ckptShift positions (counted from the window's first site; a multiple of the group size G, so block boundaries are
+// group boundaries in both sweeps and the per-site code is that of the plain kernel).  The backward sweep leaves a full
+// beta vector at the last position of every block (checkpoints, 4*Spad/2^ckptShift bytes per pair-site), the forward sweep
+// keeps alpha of the position before the current block in a per-warp scratch that stays in L2 and records every piece of
+// an IBD run (one item per run and block) together with that alpha.  The refine pass recomputes the full posterior only
+// inside those pieces.
 template <int S_T, int RQ, int G, int DEPTH, int THREADS, int MIN_BLOCKS, int SPARSE_V = 0>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const FastModel fm, const DecodeArgs args)
 {
   constexpr bool SPARSE = (SPARSE_V & 1) != 0;
   constexpr bool kSkipFwd = (SPARSE_V & 2) != 0, kSkipBwd = (SPARSE_V & 4) != 0;  // timing experiments only
-  constexpr int kGroupUnroll = SPARSE ? 1 : G / 2;
+  constexpr int kGroupUnroll = (SPARSE_V & 64) ? 1 : G / 2;  // bit 64: one copy of each step direction (code-size experiments)
   constexpr bool kSkipAlpha = (SPARSE_V & 8) != 0, kSkipBoundaryItems = (SPARSE_V & 16) != 0, kSkipRunItems = (SPARSE_V & 32) != 0;
   constexpr int S = S_T;
   constexpr int SQ = (S + 3) / 4;
@@ -418,8 +420,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
     bits.a = m.haps + static_cast<size_t>(args.hapA[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
     bits.b = m.haps + static_cast<size_t>(args.hapB[static_cast<size_t>(tile) * 32 + srcLane]) * m.wordsPerHap;
     const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowFloats;
-    // SPARSE: checkpoint slot of block b of this tile = ckptSlot0 + b
-    const long long ckptSlot0 = SPARSE ? args.tileCkptBase[tile] - (from >> ckShift) : 0;
+    // SPARSE: checkpoint slot of block b (window positions [b << ckShift, ...)) of this tile = ckptSlot0 + b
+    const long long ckptSlot0 = SPARSE ? args.tileCkptBase[tile] : 0;
     // full state vector of the warp -> [quad][lane][4] in global memory (coalesced 512-byte rows)
     auto storeVector = [&](const float (&v)[S], float4* dst) {
 #pragma unroll
@@ -428,8 +430,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
                                          4 * q + 3 < S ? v[4 * q + 3] : 0.f);
       }
     };
-    auto storeCheckpoint = [&](const float (&v)[S], const int site) {
-      storeVector(v, reinterpret_cast<float4*>(args.ckptBeta + static_cast<size_t>(ckptSlot0 + (site >> ckShift)) * kVecFloats));
+    auto storeCheckpoint = [&](const float (&v)[S], const int p) {  // beta of window position p, the last of its block
+      storeVector(v, reinterpret_cast<float4*>(args.ckptBeta + static_cast<size_t>(ckptSlot0 + (p >> ckShift)) * kVecFloats));
     };
 
     float a[S], c[S];
@@ -456,10 +458,14 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
     // ---- sweep 1: backward.  Step j handles window position len-2-j with the coefficient row of len-1-j ------------
     {
       const int steps = len - 1;
-      const int nGroups = (steps + G - 1) / G;
-      auto prefetch = [&](const int g) {  // rows of steps [gG, gG+n): window positions [len-j1, len-j0), ascending
+      // groups of G steps; SPARSE: the first group is shortened so that every later group starts at a window position
+      // p with p % G == G - 1 — then the last position of every checkpoint block is the top of a group
+      const int first = SPARSE ? min(steps, (len % G) ? (len % G) : G) : G;
+      const int nGroups = steps <= 0 ? 0 : 1 + (max(steps - first, 0) + G - 1) / G;
+      auto groupBegin = [&](const int g) { return g == 0 ? 0 : first + (g - 1) * G; };
+      auto prefetch = [&](const int g) {  // rows of the group's steps [j0, j1): window positions [len-j1, len-j0), ascending
         if (lane == 0) {
-          const int j0 = g * G, j1 = min(steps, j0 + G);
+          const int j0 = groupBegin(g), j1 = min(steps, j0 + (g == 0 ? first : G));
           const int slot = g % DEPTH;
           const uint32_t bytes = static_cast<uint32_t>(j1 - j0) * kCoefBytes;
           mbarExpectTx(&bars[slot], bytes);
@@ -474,7 +480,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
         a[k] = 1.f;
       }
       if constexpr (SPARSE) {
-        storeCheckpoint(a, from + len - 1);  // the window's last block ends at its last site (beta = ones)
+        storeCheckpoint(a, len - 1);  // the window's last block ends at its last position (beta = ones)
       }
       if (nGroups == 0) {
         // single-site window: only the all-ones record
@@ -488,10 +494,16 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
       }
       for (int g = 0; g < nGroups; ++g) {
         const int slot = g % DEPTH;
-        const int j0 = g * G;
-        const int n = min(G, steps - j0);
+        const int j0 = groupBegin(g);
+        const int n = min(g == 0 ? first : G, steps - j0);
         const float* coef = coefArea(slot);
         float4* stage = recArea(slot);
+        if constexpr (SPARSE && !kSkipBwd) {
+          // a = beta of window position len-1-j0, the top of this group: the last position of a block?
+          if (g > 0 && ((len - 1 - j0) & ckMask) == ckMask) {
+            storeCheckpoint(a, len - 1 - j0);
+          }
+        }
         if (lane == 0) {
           bulkWaitRead<DEPTH - 1>();  // the store that last read this slot's staging records has drained them
         }
@@ -511,15 +523,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
             scaleStates<S>(y, 1.0f / divisor);
           }
           stageRecord(y, stage + static_cast<size_t>(n - 1 - i) * RQ * 32, divisor);
-          if constexpr (SPARSE && !kSkipBwd) {
-            if (((from + p) & ckMask) == ckMask) {  // last site of a block
-              storeCheckpoint(y, from + p);
-            }
-          }
         };
-        // SPARSE: not unrolled, one copy of each step direction.  Unrolled over the group the two sweeps are ~7 000
-        // instructions (110 KB) of straight-line code and the kernel sits at the capacity of the instruction cache: with
-        // the sparse bookkeeping added, "no instruction" became its first stall (profiles/r2_v4_decodeNarrowSparse_ncu_full.txt).
+        // Unrolled over the group the two sweeps are ~7 000 instructions (110 KB) of straight-line code and the kernel sits
+        // at the capacity of the instruction cache: per-SITE sparse bookkeeping made "no instruction" its first stall
+        // (profiles/r2_v4_decodeNarrowSparse_ncu_full.txt), which is why that bookkeeping lives at the group tops.
 #pragma unroll(kGroupUnroll)
         for (int i = 0; i < G; i += 2) {
           if (i < n) {
@@ -540,9 +547,19 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
         if (g + DEPTH < nGroups) {
           prefetch(g + DEPTH);
         }
+        if (SPARSE && g == 0 && (n & 1)) {
+          // a shortened first group of odd size left its result in c: the groups read a
+#pragma unroll
+          for (int k = 0; k < S; ++k) {
+            a[k] = c[k];
+          }
+        }
       }
-      if (steps & 1) {
-        // beta^ of the first site ended in c
+      // where beta^ of the first site ended: the steps after the first group alternate a -> c -> a (the first group ends
+      // in a: even size, or copied above)
+      const int rest = SPARSE ? max(steps - first, 0) : steps;
+      if (rest & 1) {
+        // in c
       } else {
 #pragma unroll
         for (int k = 0; k < S; ++k) {
@@ -585,23 +602,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
       // consumers of window position p; v = alpha^(p); rec = this position's record (parking area once drained)
       auto consume = [&](const int p, const float (&v)[S], float4* rec) {
         const int site = from + p;
-        if constexpr (SPARSE && !kSkipFwd) {
-          const bool boundary = (site & ckMask) == 0 && p > 0;
-          if (boundary) {
-            // a run that continues into this block leaves the piece of the block that just ended
-            if constexpr (!kSkipBoundaryItems) {
-              if (__any_sync(kFull, runOpen)) {
-                emitItems(runOpen, (site - 1) >> ckShift, pieceStart, site - 1);
-              }
-            }
-            pieceStart = site;
-          }
-          if constexpr (!kSkipAlpha) {
-            if (boundary || p == 0) {
-              storeVector(v, alphaStart);  // same lanes read it back: no synchronisation needed
-            }
-          }
-        }
         float q[4 * RQ];  // alpha^[k] beta^[k] for k < sT (0 above); q[NR] = b_p
 #pragma unroll
         for (int qq = 0; qq < RQ; ++qq) {
@@ -638,7 +638,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
             if (__any_sync(kFull, ending || closing)) {
               // the run's last piece, then the record; the refine pass fills in the age estimates from the chain
               if constexpr (!kSkipRunItems) {
-                emitItems(ending && runOpen && pieceStart <= site - 1, (site - 1) >> ckShift, pieceStart, site - 1);
+                emitItems(ending && runOpen && pieceStart <= site - 1, (p - 1) >> ckShift, pieceStart, site - 1);
               }
               if (ending) {
                 emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, nullptr, false, chain);
@@ -650,7 +650,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
                 pieceStart = site;
               }
               if constexpr (!kSkipRunItems) {
-                emitItems(closing, site >> ckShift, pieceStart, site);
+                emitItems(closing, p >> ckShift, pieceStart, site);
               }
               if (closing) {
                 emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, nullptr,
@@ -709,6 +709,22 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
         float4* recs = recArea(slot);
         mbarWait(&bars[slot], (parity >> slot) & 1u);
         parity ^= 1u << slot;
+        if constexpr (SPARSE && !kSkipFwd) {
+          if (g > 0 && (p0 & ckMask) == 0) {
+            // a block begins with this group; c = alpha of the position before it.  A run that continues into the block
+            // leaves the piece of the block that just ended (with the alpha that was parked when that block began), then
+            // the new block's alpha is parked.  Same lanes write and read the scratch: no synchronisation needed.
+            if constexpr (!kSkipBoundaryItems) {
+              if (__any_sync(kFull, runOpen)) {
+                emitItems(runOpen, (p0 - 1) >> ckShift, pieceStart, from + p0 - 1);
+              }
+            }
+            pieceStart = from + p0;
+            if constexpr (!kSkipAlpha) {
+              storeVector(c, alphaStart);
+            }
+          }
+        }
         auto step = [&](const int i, float (&x)[S], float (&y)[S], const bool rescale) {
           const int p = p0 + i;
           const int cls = bits.cls(from + p);
@@ -722,7 +738,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
           consume(p, y, recs + static_cast<size_t>(i) * RQ * 32);
         };
 #pragma unroll(kGroupUnroll)
-        for (int i = 0; i < G; i += 2) {  // SPARSE: one copy of each step direction (instruction-cache footprint, see sweep 1)
+        for (int i = 0; i < G; i += 2) {
           if (i == 0 && g == 0) {
             // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
             const int cls = bits.cls(from);

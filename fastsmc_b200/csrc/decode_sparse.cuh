@@ -26,23 +26,26 @@ namespace fsmc
 
 constexpr int kRefineDepth = 2;
 
-// sort key of an item = its block; slots beyond the item count get the largest key
+// sort key of an item = the first site of its block (blocks are counted from the window's first site; items whose
+// blocks start at the same site share the coefficient rows); slots beyond the item count get the largest key
 __global__ void itemKeysKernel(const SparseItem* __restrict__ items, const unsigned long long* __restrict__ itemCount,
-                               const long long capacity, uint32_t* __restrict__ keys, uint32_t* __restrict__ index)
+                               const long long capacity, const int* __restrict__ tileFrom, const int ckptShift,
+                               uint32_t* __restrict__ keys, uint32_t* __restrict__ index)
 {
   const long long n = static_cast<long long>(min(*itemCount, static_cast<unsigned long long>(capacity)));
   for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < capacity;
        i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    keys[i] = i < n ? static_cast<uint32_t>(items[i].block) : 0xffffffffu;
+    keys[i] = i < n ? static_cast<uint32_t>(tileFrom[items[i].pair >> 5] + (items[i].block << ckptShift)) : 0xffffffffu;
     index[i] = static_cast<uint32_t>(i);
   }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
-// refineKernel: lane = item.  The warp sweeps the union of its items' site ranges inside one block; a lane joins the
-// backward sweep at the last site of its pair's window in the block (beta checkpoint) and the forward sweep at the first
-// one (the item's alpha), and accumulates the posterior over the item's own sites.  Lanes outside their range compute on
-// zeros / garbage, which is never looked at.
+// refineKernel: lane = item.  The 32 items of a warp share the first site of their block; the warp sweeps the block (to
+// the last site any of its pairs' windows reaches in it).  A lane joins the backward sweep at the last site of its pair's
+// window in the block (beta checkpoint); the forward sweep starts for all lanes at the block's first site, from the item's
+// alpha of the site before (or from the prior when the block is the first of the window), and every lane accumulates the
+// posterior over its item's own sites.  Lanes outside their range compute on zeros / garbage, which is never looked at.
 // ---------------------------------------------------------------------------------------------------------------------
 template <int S_T, int DEPTH, int RESCALE, int THREADS, int MIN_BLOCKS>
 __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) refineKernel(const FastModel fm, const DecodeArgs args)
@@ -105,25 +108,25 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) refineKernel(const FastMo
       const uint32_t tile = item.pair >> 5;
       tFrom = args.tileFrom[tile];
       tTo = args.tileTo[tile];
-      slot0 = args.tileCkptBase[tile] - (tFrom >> ckShift);
+      slot0 = args.tileCkptBase[tile];
       bits.a = m.haps + static_cast<size_t>(args.hapA[item.pair]) * m.wordsPerHap;
       bits.b = m.haps + static_cast<size_t>(args.hapB[item.pair]) * m.wordsPerHap;
     }
+    const int myStart = valid ? tFrom + (item.block << ckShift) : -1;  // first site of the item's block
     unsigned todo = __ballot_sync(kFull, valid);
-    while (todo) {  // the 32 items are sorted by block: one round, two where the warp straddles a block boundary
-      const int block = __shfl_sync(kFull, item.block, __ffs(todo) - 1);
-      const bool on = valid && item.block == block;
+    while (todo) {  // the 32 items are sorted by block start: one round, two where the warp straddles a boundary
+      const int lo = __shfl_sync(kFull, myStart, __ffs(todo) - 1);
+      const bool on = valid && myStart == lo;
       todo &= ~__ballot_sync(kFull, on);
-      // the pair's window inside the block, and the union over the lanes
-      const int s0 = on ? max(tFrom, block << ckShift) : 0x7fffffff;
-      const int e0 = on ? min(tTo - 1, (block << ckShift) + C - 1) : -1;
-      int lo = s0, hi = e0;
+      // last site of the pair's window inside the block, and the furthest over the lanes
+      const int e0 = on ? min(tTo - 1, lo + C - 1) : -1;
+      int hi = e0;
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) {
-        lo = min(lo, __shfl_xor_sync(kFull, lo, o));
         hi = max(hi, __shfl_xor_sync(kFull, hi, o));
       }
       const int len = hi - lo + 1;
+      const bool firstBlock = item.block == 0;  // alpha at the window's first site comes from the prior
       const float* rowBase = m.siteRows + static_cast<size_t>(lo) * kRowArrays * Spad;
       bits.word = -1;
 
@@ -145,7 +148,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) refineKernel(const FastMo
       };
       // beta at the last site of the pair's window in this block: the checkpoint of pass 1, column of the pair's lane
       auto loadBeta = [&](float (&v)[S]) {
-        loadVector(v, reinterpret_cast<const float4*>(args.ckptBeta + static_cast<size_t>(slot0 + block) * kBetaFloats) + (item.pair & 31u), 32);
+        loadVector(v, reinterpret_cast<const float4*>(args.ckptBeta + static_cast<size_t>(slot0 + item.block) * kBetaFloats) + (item.pair & 31u), 32);
       };
       auto storeRow = [&](const float (&v)[S], const int p, const int bslot) {
         if (lane == 0) {
@@ -268,16 +271,33 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) refineKernel(const FastMo
             prefetch(p + DEPTH);
           }
         };
-        // p = 0
+        // p = 0, the block's first site: one step from the parked alpha of the site before, or prior * emission when the
+        // block opens the window (ref HMM.cpp:736-743)
         {
+          const int cls = bits.cls(lo);
           mbarWait(&bars[DEPTH], coefParity & 1u);
           coefParity ^= 1u;
 #pragma unroll
           for (int k = 0; k < S; ++k) {
-            a[k] = 0.f;
+            c[k] = 0.f;
           }
-          if (on && s0 == lo) {
-            loadVector(a, alphaSrc, 1);
+          if (on && !firstBlock) {
+            loadVector(c, alphaSrc, 1);
+          }
+          forwardStep<S>(fm.colRatios, c, a, coefSlot(0), cls);
+          if (on && firstBlock) {
+            const float4* E = reinterpret_cast<const float4*>(coefSlot(0) + cls * Spad);
+#pragma unroll
+            for (int q = 0; q < SQ; ++q) {
+              const float4 e4 = E[q];
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const int k = 4 * q + i;
+                if (k < S) {
+                  a[k] = fm.prior[k] * f4(e4, i);
+                }
+              }
+            }
           }
           consume(0, a, c);
         }
@@ -289,9 +309,6 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) refineKernel(const FastMo
           const float total = forwardStep<S>(fm.colRatios, x, y, coefSlot(slot), cls);
           if ((p & (RESCALE - 1)) == 0) {
             scaleStates<S>(y, 1.0f / total);
-          }
-          if (on && s0 == lo + p) {
-            loadVector(y, alphaSrc, 1);  // this lane's window (or block) starts here
           }
           consume(p, y, x);
         };
@@ -317,8 +334,9 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) refineKernel(const FastMo
   }
 }
 
-// Per segment: sums of its chain of items (pieces in descending site order), then posterior mean and MAP as
-// HMM::getPosteriorMean / getMAP do (ref: HMM.cpp:1087-1107).
+// One warp per segment: the sums of its chain of items (pieces in descending site order; lane l adds up states l, l+32,
+// l+64: 288-byte rows read coalesced), then posterior mean and MAP as HMM::getPosteriorMean / getMAP do
+// (ref: HMM.cpp:1087-1107; the first maximum wins a tie).
 __global__ void finalizeSegmentsKernel(const DeviceModel m, fsmc_segment* __restrict__ segments,
                                        const unsigned long long* __restrict__ segmentCount, const long long segmentCapacity,
                                        const SparseItem* __restrict__ items, const float* __restrict__ itemSums,
@@ -329,40 +347,72 @@ __global__ void finalizeSegmentsKernel(const DeviceModel m, fsmc_segment* __rest
     return;  // the host re-runs the request with a larger item buffer
   }
   const int S = m.ageThreshold;
-  for (long long i = blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x; i < n;
-       i += static_cast<long long>(gridDim.x) * blockDim.x) {
-    fsmc_segment s = segments[i];
-    const int last = s.mapState;
-    s.mapState = -1;
-    if (last >= 0) {
-      float tot = 0.f;
-      for (int k = 0; k < S; ++k) {
-        float x = 0.f;
-        for (int it = last; it >= 0; it = items[it].prev) {
-          x += itemSums[static_cast<size_t>(it) * m.Spad + k];
-        }
-        tot = __fadd_rn(tot, x);
+  const int lane = threadIdx.x & 31;
+  const long long warp = (blockIdx.x * static_cast<long long>(blockDim.x) + threadIdx.x) >> 5;
+  const long long warps = (static_cast<long long>(gridDim.x) * blockDim.x) >> 5;
+  constexpr int kRounds = (kMaxParamStates + 31) / 32;
+  for (long long i = warp; i < n; i += warps) {
+    const int last = segments[i].mapState;
+    if (last < 0) {
+      if (lane == 0) {
+        segments[i].mapState = -1;
       }
-      const float norm = 1.f / tot;
-      float mean = 0.f, bestRatio = 0.f;
-      int best = 0;
-      for (int k = 0; k < S; ++k) {
-        float x = 0.f;
-        for (int it = last; it >= 0; it = items[it].prev) {
-          x += itemSums[static_cast<size_t>(it) * m.Spad + k];
+      continue;
+    }
+    float x[kRounds];
+#pragma unroll
+    for (int j = 0; j < kRounds; ++j) {
+      x[j] = 0.f;
+    }
+    for (int it = last; it >= 0; it = items[it].prev) {
+      const float* row = itemSums + static_cast<size_t>(it) * m.Spad;
+#pragma unroll
+      for (int j = 0; j < kRounds; ++j) {
+        const int k = lane + 32 * j;
+        if (k < S) {
+          x[j] += row[k];
         }
-        mean = __fadd_rn(mean, __fmul_rn(__fmul_rn(norm, x), __ldg(m.expTimes + k)));
-        const float r = x / __ldg(m.prior + k);
-        if (k == 0 || bestRatio < r) {
+      }
+    }
+    float tot = 0.f;
+#pragma unroll
+    for (int j = 0; j < kRounds; ++j) {
+      tot += x[j];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      tot += __shfl_xor_sync(kFull, tot, o);
+    }
+    const float norm = 1.f / tot;
+    float mean = 0.f, bestRatio = -1.f;
+    int best = 0x7fffffff;
+#pragma unroll
+    for (int j = 0; j < kRounds; ++j) {
+      const int k = lane + 32 * j;
+      if (k < S) {
+        mean += (norm * x[j]) * __ldg(m.expTimes + k);
+        const float r = x[j] / __ldg(m.prior + k);
+        if (r > bestRatio) {  // ascending k within the lane: the first maximum is kept
           bestRatio = r;
           best = k;
         }
       }
-      s.postMean = mean;
-      s.mapState = best;
-      s.mapTime = __ldg(m.expTimes + best);
     }
-    segments[i] = s;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      mean += __shfl_xor_sync(kFull, mean, o);
+      const float otherRatio = __shfl_xor_sync(kFull, bestRatio, o);
+      const int otherBest = __shfl_xor_sync(kFull, best, o);
+      if (otherRatio > bestRatio || (otherRatio == bestRatio && otherBest < best)) {
+        bestRatio = otherRatio;
+        best = otherBest;
+      }
+    }
+    if (lane == 0) {
+      segments[i].postMean = mean;
+      segments[i].mapState = best;
+      segments[i].mapTime = __ldg(m.expTimes + best);
+    }
   }
 }
 
