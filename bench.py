@@ -36,8 +36,9 @@ DQ = os.path.join(ROOT, "data", "30-100-2000.decodingQuantities.gz")
 FLOPS_PER_PAIR_SITE_STATE = 35  # 15 forward + 15 backward + 3 combine + 2 consume
 NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE = (6.072805e9 + 6.078759e9) / (37888 * 10000)  # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt
 NCU_DRAM_BYTES_PER_PAIR_SITE = (109.922461e9 + 109.458343e9) / (37888 * 10000)  # profiles/r1_v4_decodeFast_s69_ncu_full.txt
-# profiles/r2_v4_decodeNarrowSparse_ncu_full.txt: 90.32 GB read + 129.04 GB written by one launch over cfg2 (blocks of 32 sites)
-NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE = (90.323012e9 + 129.044333e9) / (499500 * 10000)
+# profiles/r2_final_decodeNarrowSparse_ncu_full.txt: 86.44 GB read + 100.90 GB written by one launch of decodeNarrowKernel<69, sparse>
+# over cfg2 (blocks of 128 sites); refineKernel adds 75.8 GB per step (profiles/r2_final_refine_ncu_full.txt)
+NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE = (86.442088e9 + 100.896670e9) / (499500 * 10000)
 WORKLOAD = "cfg2: all-pairs, hashing off, 1000 haplotypes x 10000 SNPs, S=69 (30-100-2000), time=50, batchSize=32"
 
 
@@ -477,7 +478,7 @@ def main():
             bytes_per_pair_site = 0.25 + 32.0 + 4.0 * ((S + 3) // 4 * 4) / sparse["block_sites"]
             kernel_name = "decodeNarrowKernel<69, sparse> (+ refineKernel<69>, finalizeSegmentsKernel: ~6 % of the step)"
             ncu_bytes = NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE
-            traffic_src = "ncu --set full capture of the kernel in this bench (profiles/r2_*_decodeNarrowSparse_ncu_full.txt)"
+            traffic_src = "ncu --set full capture of the kernel in this bench (profiles/r2_final_decodeNarrowSparse_ncu_full.txt), scaled by pair-sites"
         else:
             # the backward sweep writes beta[S] floats and the forward sweep reads them back (8*S) + 2 genotype bits
             bytes_per_pair_site = 8.0 * S + 0.25
