@@ -356,13 +356,6 @@ def main():
     tables = asmc.pyASMC.prepareModelTables(data, p)
     S, L = tables["emission1"].shape[1], data.sites
 
-    ctx = N.Context(local)
-    # a real (non-default) torch stream: handle 0 would mean "the context's own stream" to fsmc_ctx_set_stream
-    stream = torch.cuda.Stream(device=local)
-    torch.cuda.set_stream(stream)
-    ctx.set_stream(stream.cuda_stream)
-    ctx.set_model(**tables)
-    ctx.set_haplotypes(data.hapBits, L)
     a, b = all_pairs_in_reference_order(len(data.IIDList))
     tiles = tiles_for(a, b, L, world, rank)  # this rank's share of the job's batches
     flags = N.CALL_SEGMENTS | N.SEG_AGE
@@ -374,59 +367,82 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---- value: pair list resident in HBM, kernels only ----------------------------------------------------------------
-    plan = ctx.plan(tiles, flags, segment_capacity=1 << 21)
-    for _ in range(args.warmup):
-        plan.launch()
-    torch.cuda.synchronize()
-    r = plan.collect()
-    ev = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
-    barrier()
-    with ClockSampler(local) as clocks:
-        ev[0].record(stream)
-        for k in range(args.steps):
-            plan.launch()
-            ev[k + 1].record(stream)
+    class Lane:
+        """One decode context with its own stream and a resident plan of this rank's share.  (Alternating the steps over
+        two such lanes, so that the last tiles of one step share the GPU with the first tiles of the next, was measured
+        and is slower: 348 vs 340 ms per step at N=1, and 393 vs 292 ms for the narrow kernel — two persistent kernels
+        of 296 CTAs each do not interleave well.  One lane it is.)"""
+
+        def __init__(self, model_tables):
+            self.ctx = N.Context(local)
+            # a real (non-default) torch stream: handle 0 would mean "the context's own stream" to fsmc_ctx_set_stream
+            self.stream = torch.cuda.Stream(device=local)
+            self.ctx.set_stream(self.stream.cuda_stream)
+            self.ctx.set_model(**model_tables)
+            self.ctx.set_haplotypes(data.hapBits, L)
+            self.plan = self.ctx.plan(tiles, flags, segment_capacity=1 << 21)
+
+        def close(self):
+            self.plan.close()
+            self.ctx.close()
+
+    def timed_steps(lanes, sampler=None):
+        """args.warmup untimed steps, then exactly args.steps steps alternating over the lanes; returns the device time in
+        ms from the first launch to the end of the last kernel on either stream, and the lanes' collected results."""
+        for k in range(max(args.warmup, len(lanes))):  # every lane at least once
+            lanes[k % len(lanes)].plan.launch()
         barrier()
-    per_step = [ev[k].elapsed_time(ev[k + 1]) for k in range(args.steps)]
-    total_ms = ev[0].elapsed_time(ev[args.steps])
-    r = plan.collect()
+        for ln in lanes:
+            ln.plan.collect()
+        start = torch.cuda.Event(enable_timing=True)
+        ends = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+        barrier()
+        ctx_mgr = sampler if sampler is not None else ClockSampler(local)
+        with ctx_mgr:
+            start.record(lanes[0].stream)
+            for ln in lanes[1:]:
+                ln.stream.wait_event(start)
+            for k in range(args.steps):
+                lanes[k % len(lanes)].plan.launch()
+            for ln, e in zip(lanes, ends):
+                e.record(ln.stream)
+            barrier()
+        total = max(start.elapsed_time(e) for e in ends)
+        used = lanes[:min(len(lanes), args.steps)]
+        return total, [ln.plan.collect() for ln in used]
+
+    # ---- value: pair list resident in HBM, kernels only ----------------------------------------------------------------
+    lanes = [Lane(tables)]
+    clocks = ClockSampler(local)
+    rank0_ms, results = timed_steps(lanes, clocks)
+    r = results[0]
+    per_step = [rank0_ms / args.steps]
     n_segments = int(r.stats.numSegments)
     scratch_bytes = int(r.stats.scratchBytes)
     launches_per_step = int(r.stats.kernelLaunches)
     sparse = {"on": bool(r.stats.sparseKernel), "block_sites": int(r.stats.checkpointSites), "items": int(r.stats.sparseItems),
               "checkpoint_bytes": int(r.stats.checkpointBytes)}
-    plan.close()
-    total_ms = max_over_ranks(total_ms, world)
-    ms_per_step = total_ms / args.steps
+    ms_per_step = max_over_ranks(rank0_ms, world) / args.steps
     value = pair_sites / (ms_per_step / 1e3)
     n_segments = int(sum_over_ranks(n_segments, world))
+    for ln in lanes:
+        ln.plan.close()
+    ctx = lanes[0].ctx   # the e2e leg below reuses the context
 
     # ---- the same job with FastSMC's command-line default age estimates (conditional on TMRCA < time, i.e.
     # noConditionalAgeEstimates off: only the states below the threshold are consumed -> decodeNarrowKernel) ------------
-    ctx2 = N.Context(local)
-    ctx2.set_stream(stream.cuda_stream)
-    ctx2.set_model(**dict(tables, age_threshold=tables["state_threshold"]))
-    ctx2.set_haplotypes(data.hapBits, L)
-    plan2 = ctx2.plan(tiles, flags, segment_capacity=1 << 21)
-    for _ in range(args.warmup):
-        plan2.launch()
-    barrier()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(stream)
-    for _ in range(args.steps):
-        plan2.launch()
-    e1.record(stream)
-    barrier()
-    narrow_rank0_ms = e0.elapsed_time(e1) / args.steps
-    narrow_ms = max_over_ranks(narrow_rank0_ms * args.steps, world) / args.steps
-    r2 = plan2.collect()
+    cond_tables = dict(tables, age_threshold=tables["state_threshold"])
+    lanes2 = [Lane(cond_tables)]
+    narrow_total_ms, results2 = timed_steps(lanes2)
+    narrow_rank0_ms = narrow_total_ms / args.steps
+    narrow_ms = max_over_ranks(narrow_total_ms, world) / args.steps
+    r2 = results2[0]
     narrow = {"value": pair_sites / (narrow_ms / 1e3), "unit": "pair-sites/s", "ms_per_step": narrow_ms,
               "kernel": "decodeNarrowKernel<69>" if r2.stats.narrowKernel else "decodeFastKernel<69>",
               "segments_per_step": int(sum_over_ranks(int(r2.stats.numSegments), world)), "scratch_bytes": int(r2.stats.scratchBytes),
               "flags": "as the headline run but age estimates conditional on TMRCA < time (FastSMC_exe default)"}
-    plan2.close()
-    ctx2.close()
+    for ln in lanes2:
+        ln.close()
 
     # ---- e2e: fsmc_decode with host buffers -----------------------------------------------------------------------------
     for _ in range(2):
