@@ -33,6 +33,7 @@ sys.path.insert(0, ROOT)
 
 N_HAPS, N_SITES, SPAN_BP, CHROM, SEED = 1000, 10_000, 30_000_000, 1, 20201117 + 2
 DQ = os.path.join(ROOT, "data", "30-100-2000.decodingQuantities.gz")
+DQ_159 = os.path.join(ROOT, "tests", "golden", "fastsmc_example", "example.decodingQuantities.gz")  # FASTSMC_EXAMPLE table
 FLOPS_PER_PAIR_SITE_STATE = 35  # 15 forward + 15 backward + 3 combine + 2 consume
 NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE = (6.072805e9 + 6.078759e9) / (37888 * 10000)  # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt
 NCU_DRAM_BYTES_PER_PAIR_SITE = (109.922461e9 + 109.458343e9) / (37888 * 10000)  # profiles/r1_v4_decodeFast_s69_ncu_full.txt
@@ -321,6 +322,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e-run", action="store_true", help="skip the one-off FastSMC.run() wall-clock measurement")
     ap.add_argument("--no-jobs-run", action="store_true", help="skip the jobs/jobInd-partitioned hashing run (jobs_run)")
+    ap.add_argument("--no-states159", action="store_true", help="skip the 159-state legs (state-split kernels)")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", 0))
     world = int(os.environ.get("WORLD_SIZE", 1))
@@ -444,6 +446,43 @@ def main():
     for ln in lanes2:
         ln.close()
 
+    # ---- cfg2 repeated with the 159-state table of FASTSMC_EXAMPLE, rank 0's first 2 048 batches,
+    # both flag sets: the state-split kernels (decode_split.cuh) -----------------------------------------------------------
+    states159 = None
+    if rank == 0 and not args.no_states159:
+        p.decodingQuantFile = DQ_159
+        tables159 = asmc.pyASMC.prepareModelTables(data, p)
+        p.decodingQuantFile = DQ
+        S159 = tables159["emission1"].shape[1]
+        sub = {k: (v[:2048] if k != "rows" else v) for k, v in tiles.items()}
+        sub_pair_sites = float(sub["tilePairs"].sum()) * L
+        states159 = {"workload": f"cfg2's first {len(sub['tilePairs'])} batches x {L} sites with the {S159}-state example table", "states": int(S159)}
+        for label, age in (("all_state_ages", S159), ("default_flags", tables159["state_threshold"])):
+            c159 = N.Context(local)
+            st159 = torch.cuda.Stream(device=local)
+            c159.set_stream(st159.cuda_stream)
+            c159.set_model(**dict(tables159, age_threshold=age))
+            c159.set_haplotypes(data.hapBits, L)
+            pl = c159.plan(sub, flags, segment_capacity=1 << 20)
+            pl.launch()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n159 = max(1, min(3, args.steps))
+            e0.record(st159)
+            for _ in range(n159):
+                pl.launch()
+            e1.record(st159)
+            torch.cuda.synchronize()
+            ms = e0.elapsed_time(e1) / n159
+            r159 = pl.collect()
+            tf = sub_pair_sites / (ms / 1e3) * FLOPS_PER_PAIR_SITE_STATE * S159 / 1e12
+            states159[label] = {"value": sub_pair_sites / (ms / 1e3), "unit": "pair-sites/s", "ms_per_step": ms,
+                                "kernel": f"decodeSplitKernel<{int(r159.stats.statesKernel)}, {int(r159.stats.tileWarps)} warps, "
+                                          f"{'narrow' if r159.stats.narrowKernel else 'wide'}>",
+                                "fp32_tflops": tf, "fp32_frac_nominal": tf / (torch.cuda.get_device_properties(local).multi_processor_count * 128 * 2 * 1.965e9 / 1e12)}
+            pl.close()
+            c159.close()
+
     # ---- e2e: fsmc_decode with host buffers -----------------------------------------------------------------------------
     for _ in range(2):
         ctx.decode(tiles, flags, segment_capacity=1 << 21)
@@ -535,7 +574,7 @@ def main():
                                                      # 37 888 pairs x 10 000 sites), scaled by pair-sites
                                                      "traffic": NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE * my_pair_sites}),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps, "clocks": clocks.summary(),
-            "ibd_wall": ibd_wall, "jobs_run": jobs,
+            "ibd_wall": ibd_wall, "jobs_run": jobs, "states159": states159,
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
