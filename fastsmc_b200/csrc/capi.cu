@@ -310,9 +310,9 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bo
                       : rq == 2 ? fsmc::decodeNarrowKernel<69, 2, 4, kFastDepth, 128, 2, 1>
                       : rq == 3 ? fsmc::decodeNarrowKernel<69, 3, 2, kFastDepth, 128, 2, 1>
                                 : fsmc::decodeNarrowKernel<69, 4, 2, kFastDepth, 128, 2, 1>;
-    if (const char* e = std::getenv("FSMC_SPARSE_VARIANT")) {  // timing experiments (results are wrong)
+    if (const char* e = std::getenv("FSMC_SPARSE_VARIANT")) {  // development: A/B of code-size variants
       const int v = std::atoi(e);
-      if (rq == 1 && v == 65) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 65>;  // groups not unrolled
+      if (rq == 1 && v == 65) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 65>;  // groups fully unrolled
     }
     FastChoice fc{fn, 72, 128, false, true, rq};
     fc.sparse = true;
@@ -326,6 +326,9 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bo
                       : rq == 2 ? fsmc::decodeNarrowKernel<69, 2, 4, kFastDepth, 128, 2>
                       : rq == 3 ? fsmc::decodeNarrowKernel<69, 3, 2, kFastDepth, 128, 2>
                                 : fsmc::decodeNarrowKernel<69, 4, 2, kFastDepth, 128, 2>;
+    if (const char* e = std::getenv("FSMC_SPARSE_VARIANT")) {
+      if (rq == 1 && std::atoi(e) == 65) fn = fsmc::decodeNarrowKernel<69, 1, 4, kFastDepth, 128, 2, 64>;
+    }
     return FastChoice{fn, 72, 128, false, true, rq};
   }
   if (S == 69) {

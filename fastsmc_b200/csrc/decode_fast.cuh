@@ -111,30 +111,60 @@ __device__ __forceinline__ float f4(const float4& v, const int j)
 //   phase A: BU over the upper half (descending)  ||  BL over the lower half (ascending), partial results parked in y
 //   phase B: BU over the lower half (descending)  ||  BL over the upper half (ascending), each completing y
 // Same operations on the same operands as the one-chain-at-a-time form (bit-identical), same instruction count.
+#ifndef FSMC_PACKED_FP32
+#define FSMC_PACKED_FP32 1
+#endif
+// Packed fp32 (FFMA2 / FMUL2 / FADD2 of sm_100: two lanes of arithmetic per issue slot, same rounding as the scalar
+// instructions).  The kernels are issue-bound, not pipe-bound, so every operation of a step that is NOT on one of the two
+// dependent chains is done for two neighbouring states (2m, 2m+1) at once: per state a step is 2 chain FMAs + 4 halves of
+// packed instructions = 4 issue slots instead of 6, with the same operations on the same operands (bit-identical).
+__device__ __forceinline__ float2 pk(const float a, const float b)
+{
+  return make_float2(a, b);
+}
+
 template <int S> __device__ __forceinline__ void backwardStep(float (&x)[S], float (&y)[S], const float* row, const int cls)
 {
   constexpr int SQ = (S + 3) / 4, Spad = SQ * 4, QM = (SQ + 1) / 2;
+  static_assert(4 * QM < S - 1, "the lower half lies below the last state");
   const float4* E = reinterpret_cast<const float4*>(row + cls * Spad);
   const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad);
   const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad);
-  const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad);
   const float4* Rr = reinterpret_cast<const float4*>(row + 6 * Spad);
+  const float4* Us = reinterpret_cast<const float4*>(row + 7 * Spad);  // U shifted by one state: Us[k] = U[k-1]
   float bu = 0.f, bl = 0.f;
+  float above = 0.f;  // U[k] vec[k+1] for the state k the BU chain reaches next
   // phase A
 #pragma unroll
   for (int i = 0; i < QM; ++i) {
     const int qu = SQ - 1 - i;
     if (qu >= QM) {
-      const float4 e4 = E[qu], u4 = Ur[qu], r4 = Rr[qu];
+      const float4 e4 = E[qu], u4 = Us[qu], r4 = Rr[qu];
 #pragma unroll
-      for (int j = 3; j >= 0; --j) {
-        const int k = 4 * qu + j;
-        if (k < S) {
-          x[k] *= f4(e4, j);  // vec = beta(p+1) * emission(p+1), in place
+      for (int jp = 1; jp >= 0; --jp) {
+        const int k = 4 * qu + 2 * jp, k1 = k + 1;
+        if (k1 < S) {
+          // vec = beta(p+1) * emission(p+1), in place; then U[k-1] vec[k]
+          const float2 v = __fmul2_rn(pk(x[k], x[k1]), pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)));
+          x[k] = v.x;
+          x[k1] = v.y;
+          const float2 t = __fmul2_rn(pk(f4(u4, 2 * jp), f4(u4, 2 * jp + 1)), v);
+          if (k1 == S - 1) {
+            y[k1] = 0.f;  // BU[S-1] = 0
+          } else {
+            bu = fmaf(f4(r4, 2 * jp + 1), bu, above);  // BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
+            y[k1] = bu;
+          }
+          bu = fmaf(f4(r4, 2 * jp), bu, t.y);
+          y[k] = bu;
+          above = t.x;
+        } else if (k < S) {
+          x[k] *= f4(e4, 2 * jp);
+          above = f4(u4, 2 * jp) * x[k];
           if (k == S - 1) {
             y[k] = 0.f;
           } else {
-            bu = fmaf(f4(r4, j), bu, f4(u4, j) * x[k + 1]);  // BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
+            bu = fmaf(f4(r4, 2 * jp), bu, above);
             y[k] = bu;
           }
         }
@@ -144,13 +174,17 @@ template <int S> __device__ __forceinline__ void backwardStep(float (&x)[S], flo
       const int ql = i;
       const float4 e4 = E[ql], d4 = Dr[ql], b4 = Br[ql];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = 4 * ql + j;
-        if (k < S) {
-          x[k] *= f4(e4, j);
-          y[k] = fmaf(f4(d4, j), x[k], bl);  // BL[k] + D[k] vec[k], BL[k] = sum_{j<k} B[j] vec[j]
-          bl = fmaf(f4(b4, j), x[k], bl);
-        }
+      for (int jp = 0; jp < 2; ++jp) {
+        const int k = 4 * ql + 2 * jp, k1 = k + 1;
+        const float2 v = __fmul2_rn(pk(x[k], x[k1]), pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)));
+        x[k] = v.x;
+        x[k1] = v.y;
+        const float bl0 = bl;
+        const float bl1 = fmaf(f4(b4, 2 * jp), v.x, bl0);  // BL[k+1] = BL[k] + B[k] vec[k]
+        bl = fmaf(f4(b4, 2 * jp + 1), v.y, bl1);
+        const float2 w = __ffma2_rn(pk(f4(d4, 2 * jp), f4(d4, 2 * jp + 1)), v, pk(bl0, bl1));  // BL[k] + D[k] vec[k]
+        y[k] = w.x;
+        y[k1] = w.y;
       }
     }
   }
@@ -159,27 +193,36 @@ template <int S> __device__ __forceinline__ void backwardStep(float (&x)[S], flo
   for (int i = 0; i < QM; ++i) {
     {
       const int ql = QM - 1 - i;
-      const float4 u4 = Ur[ql], r4 = Rr[ql];
+      const float4 u4 = Us[ql], r4 = Rr[ql];
 #pragma unroll
-      for (int j = 3; j >= 0; --j) {
-        const int k = 4 * ql + j;
-        if (k < S - 1) {
-          bu = fmaf(f4(r4, j), bu, f4(u4, j) * x[k + 1]);
-          y[k] += bu;
-        } else if (k == S - 1) {
-          // (only when the whole vector is one quad wide)
-        }
+      for (int jp = 1; jp >= 0; --jp) {
+        const int k = 4 * ql + 2 * jp, k1 = k + 1;
+        const float2 t = __fmul2_rn(pk(f4(u4, 2 * jp), f4(u4, 2 * jp + 1)), pk(x[k], x[k1]));
+        const float b1 = fmaf(f4(r4, 2 * jp + 1), bu, above);
+        const float b0 = fmaf(f4(r4, 2 * jp), b1, t.y);
+        bu = b0;
+        above = t.x;
+        const float2 w = __fadd2_rn(pk(y[k], y[k1]), pk(b0, b1));
+        y[k] = w.x;
+        y[k1] = w.y;
       }
     }
     const int qu = QM + i;
     if (qu < SQ) {
       const float4 d4 = Dr[qu], b4 = Br[qu];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = 4 * qu + j;
-        if (k < S) {
-          y[k] = fmaf(f4(d4, j), x[k], bl) + y[k];
-          bl = fmaf(f4(b4, j), x[k], bl);
+      for (int jp = 0; jp < 2; ++jp) {
+        const int k = 4 * qu + 2 * jp, k1 = k + 1;
+        if (k1 < S) {
+          const float bl0 = bl;
+          const float bl1 = fmaf(f4(b4, 2 * jp), x[k], bl0);
+          bl = fmaf(f4(b4, 2 * jp + 1), x[k1], bl1);
+          const float2 w = __fadd2_rn(__ffma2_rn(pk(f4(d4, 2 * jp), f4(d4, 2 * jp + 1)), pk(x[k], x[k1]), pk(bl0, bl1)),
+                                      pk(y[k], y[k1]));
+          y[k] = w.x;
+          y[k1] = w.y;
+        } else if (k < S) {
+          y[k] = fmaf(f4(d4, 2 * jp), x[k], bl) + y[k];
         }
       }
     }
@@ -188,22 +231,35 @@ template <int S> __device__ __forceinline__ void backwardStep(float (&x)[S], flo
 
 template <int S> __device__ __forceinline__ float sumStates(const float (&a)[S])
 {
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  // four partial sums over the states k % 4, as two packed accumulators
+  float2 s01 = pk(0.f, 0.f), s23 = pk(0.f, 0.f);
 #pragma unroll
   for (int k = 0; k < S; k += 4) {
-    s0 += a[k];
-    if (k + 1 < S) s1 += a[k + 1];
-    if (k + 2 < S) s2 += a[k + 2];
-    if (k + 3 < S) s3 += a[k + 3];
+    if (k + 1 < S) {
+      s01 = __fadd2_rn(s01, pk(a[k], a[k + 1]));
+    } else {
+      s01.x += a[k];
+    }
+    if (k + 3 < S) {
+      s23 = __fadd2_rn(s23, pk(a[k + 2], a[k + 3]));
+    } else if (k + 2 < S) {
+      s23.x += a[k + 2];
+    }
   }
-  return (s0 + s1) + (s2 + s3);
+  return (s01.x + s01.y) + (s23.x + s23.y);
 }
 
 template <int S> __device__ __forceinline__ void scaleStates(float (&a)[S], const float sc)
 {
 #pragma unroll
-  for (int k = 0; k < S; ++k) {
-    a[k] *= sc;
+  for (int k = 0; k < S; k += 2) {
+    if (k + 1 < S) {
+      const float2 v = __fmul2_rn(pk(a[k], a[k + 1]), pk(sc, sc));
+      a[k] = v.x;
+      a[k + 1] = v.y;
+    } else {
+      a[k] *= sc;
+    }
   }
 }
 
@@ -229,10 +285,16 @@ __device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[
       const int ql = i;
       const float4 d4 = Dr[ql], u4 = Ur[ql];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = 4 * ql + j;
-        y[k] = fmaf(f4(d4, j), x[k], au);                   // AU[k] + D[k] x[k]
-        au = fmaf(colRatios[k], au, f4(u4, j) * x[k]);      // AU[k+1] = U[k] x[k] + colRatio[k] AU[k]
+      for (int jp = 0; jp < 2; ++jp) {
+        const int k = 4 * ql + 2 * jp, k1 = k + 1;
+        const float2 xx = pk(x[k], x[k1]);
+        const float2 t = __fmul2_rn(pk(f4(u4, 2 * jp), f4(u4, 2 * jp + 1)), xx);
+        const float au0 = au;
+        const float au1 = fmaf(colRatios[k], au0, t.x);  // AU[k+1] = U[k] x[k] + colRatio[k] AU[k]
+        au = fmaf(colRatios[k1], au1, t.y);
+        const float2 w = __ffma2_rn(pk(f4(d4, 2 * jp), f4(d4, 2 * jp + 1)), xx, pk(au0, au1));  // AU[k] + D[k] x[k]
+        y[k] = w.x;
+        y[k1] = w.y;
       }
     }
     const int qu = SQ - 1 - i;
@@ -254,12 +316,22 @@ __device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[
     if (qu < SQ) {
       const float4 d4 = Dr[qu], u4 = Ur[qu], e4 = E[qu], b4 = Br[qu];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) {
-        const int k = 4 * qu + j;
-        if (k < S) {
-          const float t = fmaf(f4(d4, j), x[k], au);
-          y[k] = f4(e4, j) * (k < S - 1 ? fmaf(f4(b4, j), y[k], t) : t);
-          au = fmaf(colRatios[k], au, f4(u4, j) * x[k]);
+      for (int jp = 0; jp < 2; ++jp) {
+        const int k = 4 * qu + 2 * jp, k1 = k + 1;
+        if (k1 < S) {
+          const float2 xx = pk(x[k], x[k1]);
+          const float2 t = __fmul2_rn(pk(f4(u4, 2 * jp), f4(u4, 2 * jp + 1)), xx);
+          const float au0 = au;
+          const float au1 = fmaf(colRatios[k], au0, t.x);
+          au = fmaf(colRatios[k1], au1, t.y);
+          const float2 tt = __ffma2_rn(pk(f4(d4, 2 * jp), f4(d4, 2 * jp + 1)), xx, pk(au0, au1));
+          // (the last state's suffix sum is 0: its B term adds nothing, as in the reference's special case)
+          const float2 w = __fmul2_rn(pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)),
+                                      __ffma2_rn(pk(f4(b4, 2 * jp), f4(b4, 2 * jp + 1)), pk(y[k], y[k1]), tt));
+          y[k] = w.x;
+          y[k1] = w.y;
+        } else if (k < S) {
+          y[k] = f4(e4, 2 * jp) * fmaf(f4(d4, 2 * jp), x[k], au);  // k == S-1 (S odd)
         }
       }
     }
@@ -267,10 +339,15 @@ __device__ __forceinline__ float forwardStep(const float* colRatios, float (&x)[
       const int ql = QM - 1 - i;
       const float4 e4 = E[ql], b4 = Br[ql];
 #pragma unroll
-      for (int j = 3; j >= 0; --j) {
-        const int k = 4 * ql + j;
-        y[k] = f4(e4, j) * fmaf(f4(b4, j), run, y[k]);
-        run += x[k];
+      for (int jp = 1; jp >= 0; --jp) {
+        const int k = 4 * ql + 2 * jp, k1 = k + 1;
+        const float s1 = run;  // sum_{j>k1} x[j]
+        const float s0 = s1 + x[k1];
+        run = s0 + x[k];
+        const float2 w = __fmul2_rn(pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)),
+                                    __ffma2_rn(pk(f4(b4, 2 * jp), f4(b4, 2 * jp + 1)), pk(s0, s1), pk(y[k], y[k1])));
+        y[k] = w.x;
+        y[k1] = w.y;
       }
     }
   }
@@ -352,7 +429,10 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
 {
   constexpr bool SPARSE = (SPARSE_V & 1) != 0;
   constexpr bool kSkipFwd = (SPARSE_V & 2) != 0, kSkipBwd = (SPARSE_V & 4) != 0;  // timing experiments only
-  constexpr int kGroupUnroll = (SPARSE_V & 64) ? 1 : G / 2;  // bit 64: one copy of each step direction (code-size experiments)
+  // One copy of each step pair per sweep: the site loops stream from the instruction cache.  Fully unrolled over the group
+  // (bit 64, kept for A/B runs) the kernel is ~100 KB of straight-line code and `no_instruction` is its first stall
+  // (profiles/r2_p1_decodeNarrowSparse_packed_unrolled_ncu_full.txt: 1.61 warps per issue; 346 -> 294 ms per cfg2 step without the unrolling).
+  constexpr int kGroupUnroll = (SPARSE_V & 64) ? G / 2 : 1;
   constexpr bool kSkipAlpha = (SPARSE_V & 8) != 0, kSkipBoundaryItems = (SPARSE_V & 16) != 0, kSkipRunItems = (SPARSE_V & 32) != 0;
   constexpr int S = S_T;
   constexpr int SQ = (S + 3) / 4;
@@ -524,8 +604,7 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeNarrowKernel(const 
           }
           stageRecord(y, stage + static_cast<size_t>(n - 1 - i) * RQ * 32, divisor);
         };
-        // Unrolled over the group the two sweeps are ~7 000 instructions (110 KB) of straight-line code and the kernel sits
-        // at the capacity of the instruction cache: per-SITE sparse bookkeeping made "no instruction" its first stall
+        // The kernel is bound by instruction supply: per-SITE sparse bookkeeping made "no instruction" its first stall
         // (profiles/r2_v4_decodeNarrowSparse_ncu_full.txt), which is why that bookkeeping lives at the group tops.
 #pragma unroll(kGroupUnroll)
         for (int i = 0; i < G; i += 2) {

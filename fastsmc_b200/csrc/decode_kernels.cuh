@@ -28,7 +28,7 @@
 namespace fsmc
 {
 
-constexpr int kRowArrays = 7;  // per-site table row: E_homMajor, E_het, E_homMinor, D, B, U, RR (each Spad floats)
+constexpr int kRowArrays = 8;  // per-site table row: E_homMajor, E_het, E_homMinor, D, B, U, RR, U shifted by one state (each Spad floats)
 constexpr unsigned kFull = 0xffffffffu;
 
 struct DeviceModel {
@@ -626,7 +626,8 @@ __global__ void __launch_bounds__(THREADS, MIN_BLOCKS) decodeTilesKernel(const D
 
 // -------------------------------------------------------------------------------------------------
 // model assembly: gather the distance-keyed transition rows and the three emission classes into one
-// contiguous row per site: [E_homMajor | E_het | E_homMinor | D | B | U | RR], each Spad floats.
+// contiguous row per site: [E_homMajor | E_het | E_homMinor | D | B | U | RR | Us], each Spad floats; Us[k] = U[k-1]
+// (the packed backward step multiplies U[k-1] vec[k] for two neighbouring states at once, decode_fast.cuh).
 // E_homMajor = e1 + e0m1, E_het = e1, E_homMinor = (e1 + e0m1) + e2m0 are bit-identical to the
 // reference's e1 + e0m1*isZero + e2m0*isTwo for the three genotype classes (ref HMM.cpp:827-828).
 // -------------------------------------------------------------------------------------------------
@@ -642,7 +643,7 @@ static __global__ void buildSiteRowsKernel(const int S, const int Spad, const in
     const int site = static_cast<int>(i / Spad);
     const int k = static_cast<int>(i % Spad);
     float* out = rows + static_cast<size_t>(site) * kRowArrays * Spad + k;
-    float v[kRowArrays] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float v[kRowArrays] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (k < S) {
       const size_t e = static_cast<size_t>(site) * S + k;
       const float hm = __fadd_rn(e1[e], e0m1[e]);
@@ -655,6 +656,9 @@ static __global__ void buildSiteRowsKernel(const int S, const int Spad, const in
         v[4] = B[t];
         v[5] = U[t];
         v[6] = RR[t];
+        if (k > 0) {
+          v[7] = U[t - 1];
+        }
       }
     }
 #pragma unroll
