@@ -77,18 +77,32 @@ __device__ __forceinline__ float forwardSplit(const float* __restrict__ colRatio
           b4 = Br[q];
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = 4 * q + j, k = K0 + i;
-          if (k < S) {
-            if (LOWER) {
-              y[i] = fmaf(f4(d4, j), x[i], au);  // AU[k] + D[k] x[k]
-            } else {
-              const float t = fmaf(f4(d4, j), x[i], au);
-              y[i] = f4(e4, j) * (k < S - 1 ? fmaf(f4(b4, j), y[i], t) : t);
+        for (int jp = 0; jp < 2; ++jp) {
+          const int i = 4 * q + 2 * jp, k = K0 + i;
+          if (k + 1 < S) {
+            // two neighbouring states per packed instruction; only the AU chain itself is scalar (decode_fast.cuh)
+            const float2 xx = pk(x[i], x[i + 1]);
+            const float2 t = __fmul2_rn(pk(f4(u4, 2 * jp), f4(u4, 2 * jp + 1)), xx);
+            const float au0 = au;
+            const float au1 = fmaf(colRatios[k], au0, t.x);  // AU[k+1] = U[k] x[k] + colRatio[k] AU[k]
+            au = fmaf(colRatios[k + 1], au1, t.y);
+            float2 w = __ffma2_rn(pk(f4(d4, 2 * jp), f4(d4, 2 * jp + 1)), xx, pk(au0, au1));  // AU[k] + D[k] x[k]
+            if (!LOWER) {
+              // (the last state's suffix sum is 0, so its B term adds nothing)
+              w = __fmul2_rn(pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)),
+                             __ffma2_rn(pk(f4(b4, 2 * jp), f4(b4, 2 * jp + 1)), pk(y[i], y[i + 1]), w));
             }
-            au = fmaf(colRatios[k], au, f4(u4, j) * x[i]);  // AU[k+1] = U[k] x[k] + colRatio[k] AU[k]
+            y[i] = w.x;
+            y[i + 1] = w.y;
           } else {
-            y[i] = 0.f;
+            if (k < S) {
+              const float t = fmaf(f4(d4, 2 * jp), x[i], au);
+              y[i] = LOWER ? t : f4(e4, 2 * jp) * (k < S - 1 ? fmaf(f4(b4, 2 * jp), y[i], t) : t);
+              au = fmaf(colRatios[k < S ? k : 0], au, f4(u4, 2 * jp) * x[i]);
+            } else {
+              y[i] = 0.f;
+            }
+            y[i + 1] = 0.f;
           }
         }
       }
@@ -106,11 +120,25 @@ __device__ __forceinline__ float forwardSplit(const float* __restrict__ colRatio
           b4 = Br[q];
         }
 #pragma unroll
-        for (int j = 3; j >= 0; --j) {
-          const int i = 4 * q + j, k = K0 + i;
-          if (k < S) {
+        for (int jp = 1; jp >= 0; --jp) {
+          const int i = 4 * q + 2 * jp, k = K0 + i;
+          if (k + 1 < S) {
+            const float s1 = run;  // sum_{j>k+1} x[j]
+            const float s0 = s1 + x[i + 1];
+            run = s0 + x[i];
             if (LOWER) {
-              y[i] = f4(e4, j) * fmaf(f4(b4, j), run, y[i]);  // E (AU + D x + B sum_{j>k} x[j])
+              // E (AU + D x + B sum_{j>k} x[j])
+              const float2 w = __fmul2_rn(pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)),
+                                          __ffma2_rn(pk(f4(b4, 2 * jp), f4(b4, 2 * jp + 1)), pk(s0, s1), pk(y[i], y[i + 1])));
+              y[i] = w.x;
+              y[i + 1] = w.y;
+            } else {
+              y[i] = s0;
+              y[i + 1] = s1;
+            }
+          } else if (k < S) {
+            if (LOWER) {
+              y[i] = f4(e4, 2 * jp) * fmaf(f4(b4, 2 * jp), run, y[i]);
             } else {
               y[i] = run;
             }
@@ -147,7 +175,7 @@ __device__ __forceinline__ void backwardSplit(float (&x)[SplitGeom<S, NW>::SEG],
   const float4* E = reinterpret_cast<const float4*>(row + cls * Spad) + Q0;
   const float4* Dr = reinterpret_cast<const float4*>(row + 3 * Spad) + Q0;
   const float4* Br = reinterpret_cast<const float4*>(row + 4 * Spad) + Q0;
-  const float4* Ur = reinterpret_cast<const float4*>(row + 5 * Spad) + Q0;
+  const float4* Us = reinterpret_cast<const float4*>(row + 7 * Spad) + Q0;  // U shifted by one state
   const float4* Rr = reinterpret_cast<const float4*>(row + 6 * Spad) + Q0;
 #pragma unroll
   for (int s = 0; s < NW; ++s) {
@@ -161,16 +189,32 @@ __device__ __forceinline__ void backwardSplit(float (&x)[SplitGeom<S, NW>::SEG],
           e4 = E[q];
         }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const int i = 4 * q + j, k = K0 + i;
-          if (k < S) {
+        for (int jp = 0; jp < 2; ++jp) {
+          const int i = 4 * q + 2 * jp, k = K0 + i;
+          if (k + 1 < S) {
+            float2 v = pk(x[i], x[i + 1]);
             if (LOWER) {
-              x[i] *= f4(e4, j);                 // vec = beta(p+1) * emission(p+1)
-              y[i] = fmaf(f4(d4, j), x[i], bl);  // BL[k] + D[k] vec[k]
-            } else {
-              y[i] = fmaf(f4(d4, j), x[i], bl) + y[i];
+              v = __fmul2_rn(v, pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)));  // vec = beta(p+1) * emission(p+1)
+              x[i] = v.x;
+              x[i + 1] = v.y;
             }
-            bl = fmaf(f4(b4, j), x[i], bl);  // BL[k+1] = BL[k] + B[k] vec[k]
+            const float bl0 = bl;
+            const float bl1 = fmaf(f4(b4, 2 * jp), v.x, bl0);  // BL[k+1] = BL[k] + B[k] vec[k]
+            bl = fmaf(f4(b4, 2 * jp + 1), v.y, bl1);
+            float2 w = __ffma2_rn(pk(f4(d4, 2 * jp), f4(d4, 2 * jp + 1)), v, pk(bl0, bl1));  // BL[k] + D[k] vec[k]
+            if (!LOWER) {
+              w = __fadd2_rn(w, pk(y[i], y[i + 1]));
+            }
+            y[i] = w.x;
+            y[i + 1] = w.y;
+          } else if (k < S) {
+            if (LOWER) {
+              x[i] *= f4(e4, 2 * jp);
+              y[i] = fmaf(f4(d4, 2 * jp), x[i], bl);
+            } else {
+              y[i] = fmaf(f4(d4, 2 * jp), x[i], bl) + y[i];
+            }
+            bl = fmaf(f4(b4, 2 * jp), x[i], bl);
           }
         }
       }
@@ -180,35 +224,66 @@ __device__ __forceinline__ void backwardSplit(float (&x)[SplitGeom<S, NW>::SEG],
     }
     if (s == NW - 1 - GID) {
       float bu = GID == NW - 1 ? 0.f : xc[kXDesc][GID][lane];
-      const float above = GID == NW - 1 ? 0.f : xc[kXVec][GID][lane];  // vec of the first state of the next warp
+      // U[k] vec[k+1] for the state k the BU chain reaches next; across the warp boundary: vec of the next warp's first state
+      float above = 0.f;
+      if (GID < NW - 1) {
+        above = Us[SEGQ].x * xc[kXVec][GID][lane];  // Us[k] = U[k-1]
+      }
 #pragma unroll
       for (int q = SEGQ - 1; q >= 0; --q) {
-        const float4 u4 = Ur[q], r4 = Rr[q];
+        const float4 u4 = Us[q], r4 = Rr[q];
         float4 e4 = make_float4(0.f, 0.f, 0.f, 0.f);
         if (!LOWER) {
           e4 = E[q];
         }
 #pragma unroll
-        for (int j = 3; j >= 0; --j) {
-          const int i = 4 * q + j, k = K0 + i;
-          if (k < S) {
+        for (int jp = 1; jp >= 0; --jp) {
+          const int i = 4 * q + 2 * jp, k = K0 + i;
+          if (k + 1 < S) {
+            float2 v = pk(x[i], x[i + 1]);
             if (!LOWER) {
-              x[i] *= f4(e4, j);
+              v = __fmul2_rn(v, pk(f4(e4, 2 * jp), f4(e4, 2 * jp + 1)));
+              x[i] = v.x;
+              x[i + 1] = v.y;
             }
-            if (k == S - 1) {
-              y[i] = 0.f;  // BU[S-1] = 0
+            const float2 t = __fmul2_rn(pk(f4(u4, 2 * jp), f4(u4, 2 * jp + 1)), v);  // U[k-1] vec[k]
+            float b1 = 0.f;  // BU[S-1] = 0
+            if (k + 1 < S - 1) {
+              b1 = fmaf(f4(r4, 2 * jp + 1), bu, above);  // BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
+            }
+            const float b0 = fmaf(f4(r4, 2 * jp), b1, t.y);
+            bu = b0;
+            above = t.x;
+            if (LOWER) {
+              const float2 w = __fadd2_rn(pk(y[i], y[i + 1]), pk(b0, b1));
+              y[i] = w.x;
+              y[i + 1] = w.y;
             } else {
-              const float next = i + 1 < SEG ? x[i + 1 < SEG ? i + 1 : i] : above;
-              bu = fmaf(f4(r4, j), bu, f4(u4, j) * next);  // BU[k] = U[k] vec[k+1] + RR[k] BU[k+1]
-              if (LOWER) {
-                y[i] += bu;
-              } else {
-                y[i] = bu;
-              }
+              y[i] = b0;
+              y[i + 1] = b1;
             }
           } else {
-            x[i] = 0.f;
-            y[i] = 0.f;
+            if (k < S) {
+              if (!LOWER) {
+                x[i] *= f4(e4, 2 * jp);
+              }
+              above = f4(u4, 2 * jp) * x[i];
+              float b0 = 0.f;
+              if (k < S - 1) {
+                b0 = fmaf(f4(r4, 2 * jp), bu, above);
+              }
+              bu = b0;
+              if (LOWER) {
+                y[i] += b0;
+              } else {
+                y[i] = b0;
+              }
+            } else {
+              x[i] = 0.f;
+              y[i] = 0.f;
+            }
+            x[i + 1] = 0.f;
+            y[i + 1] = 0.f;
           }
         }
       }
@@ -435,7 +510,8 @@ __device__ __forceinline__ void splitBody(const FastModel& fm, const DecodeArgs&
             }
             xp ^= 1;
           };
-#pragma unroll
+          // (not unrolled: one copy of the step pair per sweep keeps the four warps' bodies in the instruction cache)
+#pragma unroll 1
           for (int i = 0; i < GRP; i += 2) {
             if (i < n) {
               step(i, a, c);
@@ -624,7 +700,7 @@ __device__ __forceinline__ void splitBody(const FastModel& fm, const DecodeArgs&
           } else {
             step(0, c, a);
           }
-#pragma unroll
+#pragma unroll 1
           for (int i = 1; i < GRP; i += 2) {
             if (i < n) {
               step(i, a, c);
