@@ -115,6 +115,7 @@ struct SeedKey {
   uint32_t window[4];
   int32_t lastJob, aboveDiag;
   uint32_t flags;
+  int32_t maxSeeds, readAhead;
 };
 
 struct fsmc_ctx {
@@ -148,6 +149,10 @@ struct fsmc_ctx {
   DevBuf<fsmc_match> seedOut;
   DevBuf<uint32_t> seedRank;              // [W][H] seed-map iteration ranks (FSMC_SEED_REFERENCE_ORDER)
   DevBuf<unsigned char> seedLowComplexity; // [W] low-complexity flags (fsmc_seed_params.skip)
+  // max_seeds > 0: registration keys (seed_kernels.cuh, nestedKeysKernels)
+  DevBuf<uint32_t> seedRep0, seedCur;      // [W][H]
+  DevBuf<unsigned char> seedDepth;         // [W][H]
+  DevBuf<uint64_t> seedRegKeyT, seedRegKeys;  // [W][H], [H][W]
   fsmc::CandidateOrderer orderer;         // device-side reference candidate order (seed_order.h)
   const fsmc_match* orderedOut = nullptr; // its result, valid until the next fsmc_seed call
   bool seedCacheValid = false;  // seedOut holds every interval of the last fsmc_seed call (which overflowed the caller)
@@ -1153,6 +1158,9 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   if (!sp->geneticPositions || !sp->globalHapId || sp->gap < 0) {
     return fail(FSMC_E_INVALID, "fsmc_seed: geneticPositions / globalHapId missing or negative gap");
   }
+  if (sp->maxSeeds < 0 || (sp->maxSeeds > 0 && (sp->readAhead < 1 || sp->readAhead > 127))) {
+    return fail(FSMC_E_INVALID, "fsmc_seed: maxSeeds must be >= 0 and, when set, readAhead in [1, 127]");
+  }
   FSMC_CUDA(cudaSetDevice(ctx->device));
   cudaStream_t st = ctx->stream;
   const uint32_t H = static_cast<uint32_t>(ctx->numHaps);
@@ -1185,6 +1193,8 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
   key.lastJob = sp->lastJob;
   key.aboveDiag = sp->aboveDiag;
   key.flags = sp->flags;
+  key.maxSeeds = sp->maxSeeds;
+  key.readAhead = sp->readAhead;
   const bool cacheHit = ctx->seedCacheValid && std::memcmp(&key, &ctx->seedCacheKey, sizeof key) == 0 &&
                         capacity >= ctx->seedCacheStats.numMatches;
   if (!cacheHit) {
@@ -1300,10 +1310,12 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
     }
     if (refOrder && W > 0) {
       const uint64_t* flip = sp->flipMask;
-      rankThread = std::thread([&hostKeys, &hostRank, &rankMs, flip, H, W] {
+      const int maxSeeds = sp->maxSeeds, readAhead = sp->readAhead;
+      rankThread = std::thread([&hostKeys, &hostRank, &rankMs, flip, H, W, maxSeeds, readAhead] {
         const auto t0 = std::chrono::steady_clock::now();
         hostRank = candidate_order::seedGroupRanks(
-            H, W, [&](const uint32_t h, const int w) { return hostKeys[static_cast<size_t>(w) * H + h] ^ (flip ? flip[w] : 0ull); });
+            H, W, [&](const uint32_t h, const int w) { return hostKeys[static_cast<size_t>(w) * H + h] ^ (flip ? flip[w] : 0ull); }, 0,
+            maxSeeds, readAhead);
         rankMs = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
       });
     }
@@ -1316,6 +1328,68 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
         }
       }
     } joiner{rankThread};
+    // max_seeds > 0: registration keys of every (word, haplotype) replace the words (seed_kernels.cuh)
+    a.nested = 0;
+    a.maxDepth = 0;
+    if (sp->maxSeeds > 0 && W > 0) {
+      const size_t WH = static_cast<size_t>(W) * H;
+      FSMC_CUDA(ctx->seedRep0.ensure(WH));
+      FSMC_CUDA(ctx->seedCur.ensure(WH));
+      FSMC_CUDA(ctx->seedDepth.ensure(WH));
+      FSMC_CUDA(ctx->seedRegKeyT.ensure(WH));
+      FSMC_CUDA(ctx->seedRegKeys.ensure(WH));
+      fsmc::NestArgs na{};
+      na.H = H;
+      na.W = W;
+      na.C = C;
+      na.maxSeeds = sp->maxSeeds;
+      na.readAhead = sp->readAhead;
+      na.owner = a.owner;
+      na.slotCount = a.slotCount;
+      na.slotOf = a.slotOf;
+      na.rep0 = ctx->seedRep0.p;
+      na.cur = ctx->seedCur.p;
+      na.depth = ctx->seedDepth.p;
+      na.pending = ctx->seedCounters.p + 7;
+      na.regKeyT = ctx->seedRegKeyT.p;
+      for (int level = 0; level < sp->readAhead; ++level) {
+        FSMC_CUDA(cudaMemsetAsync(na.pending, 0, sizeof(unsigned long long), st));
+        na.level = level;
+        for (int w0 = 0; w0 < W; w0 += WB) {
+          const unsigned nw = static_cast<unsigned>(std::min(WB, W - w0));
+          const long long perWordCap = std::max<long long>(1, sms * 8ll / nw);
+          const unsigned hapBlocks = static_cast<unsigned>(std::min<long long>((H + 255ll) / 256, perWordCap));
+          a.wordBase = na.wordBase = w0;
+          a.wordsInBatch = static_cast<int>(nw);
+          FSMC_CUDA(cudaMemsetAsync(a.owner, 0, sizeof(uint32_t) * C * nw, st));
+          FSMC_CUDA(cudaMemsetAsync(a.slotCount, 0, sizeof(uint32_t) * C * nw, st));
+          if (level == 0) {
+            fsmc::groupInsertKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
+            fsmc::nestLevel0Kernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(na);
+          } else {
+            fsmc::nestInsertKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(na);
+            fsmc::nestFinishKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(na);
+          }
+          launches += 2;
+        }
+        unsigned long long pending = 0;
+        FSMC_CUDA(cudaMemcpyAsync(&pending, na.pending, sizeof pending, cudaMemcpyDeviceToHost, st));
+        FSMC_CUDA(cudaStreamSynchronize(st));
+        if (pending == 0) {
+          break;
+        }
+      }
+      fsmc::nestEmitKernel<<<sms * 4, 256, 0, st>>>(na);
+      const dim3 tb(32, 8), tg((H + 31) / 32, (W + 31) / 32);
+      fsmc::transposeKeysBackKernel<<<tg, tb, 0, st>>>(ctx->seedRegKeyT.p, H, W, ctx->seedRegKeys.p);
+      launches += 2;
+      FSMC_CUDA(cudaGetLastError());
+      a.keysT = ctx->seedRegKeyT.p;
+      a.haps = ctx->seedRegKeys.p;
+      a.wordsPerHap = W;
+      a.nested = 1;
+      a.maxDepth = sp->readAhead - 1;
+    }
     unsigned long long counters[8] = {0};
     for (int attempt = 0; attempt < 2; ++attempt) {
       a.out = ctx->seedOut.p;
@@ -1337,7 +1411,11 @@ int fsmc_seed(fsmc_ctx* ctx, const fsmc_seed_params* sp, fsmc_match* out, const 
         fsmc::groupScanKernel<<<nw, 1024, 0, st>>>(a);
         fsmc::groupScatterKernel<<<dim3(hapBlocks, nw), 256, 0, st>>>(a);
         fsmc::batchChunksKernel<<<1, 32, 0, st>>>(a);
-        fsmc::pairExtendKernel<<<sms * 8, fsmc::kPairBlockThreads, 0, st>>>(a);
+        if (a.nested) {
+          fsmc::pairExtendKernel<true><<<sms * 8, fsmc::kPairBlockThreads, 0, st>>>(a);
+        } else {
+          fsmc::pairExtendKernel<false><<<sms * 8, fsmc::kPairBlockThreads, 0, st>>>(a);
+        }
         launches += 6;
       }
       FSMC_CUDA(cudaGetLastError());

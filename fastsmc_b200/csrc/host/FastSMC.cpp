@@ -53,9 +53,15 @@ void ASMC::FastSMC::seedAndDecode()
   if (mParams.hashingWordSize != 64) {
     throw std::runtime_error("only 64-SNP hashing words are supported");
   }
-  if (mParams.max_seeds != 0 || mParams.min_maf != 0.f || !mParams.haploid) {
-    throw std::runtime_error("the B200 build does not support max_seeds > 0, min_maf > 0 or diploid hashing "
-                             "(gap, min_m and skip are free)");
+  if (mParams.min_maf != 0.f || !mParams.haploid) {
+    throw std::runtime_error("the B200 build does not support min_maf > 0 or diploid hashing "
+                             "(gap, min_m, skip and max_seeds are free)");
+  }
+  if (mParams.max_seeds < 0) {
+    throw std::runtime_error("max_seeds must be >= 0");
+  }
+  if (mParams.max_seeds > 0 && mParams.referenceCandidateOrder && std::getenv("FSMC_HOST_ORDER") != nullptr) {
+    throw std::runtime_error("max_seeds > 0 needs the device candidate order (unset FSMC_HOST_ORDER)");
   }
   if (mParams.skip > 0.f && mParams.referenceCandidateOrder && std::getenv("FSMC_HOST_ORDER") != nullptr) {
     throw std::runtime_error("skip > 0 needs the device candidate order (unset FSMC_HOST_ORDER)");
@@ -81,6 +87,8 @@ void ASMC::FastSMC::seedAndDecode()
   const bool deviceOrder = mParams.referenceCandidateOrder && !hostOrder;
   sp.flipMask = mData.flipMask.data();
   sp.skip = mParams.skip;
+  sp.maxSeeds = mParams.max_seeds;
+  sp.readAhead = mParams.constReadAhead;
   sp.flags = deviceOrder ? FSMC_SEED_REFERENCE_ORDER
                          : (mParams.referenceCandidateOrder ? (FSMC_SEED_ALL_INTERVALS | FSMC_SEED_UNSORTED) : 0u);
 

@@ -220,8 +220,13 @@ template <class Fn> void parallelForWords(const int numWords, unsigned threads, 
 // this order and enumerates a bucket's pairs (i < ii) in haplotype order, so (rank, a, b) is the creation order of the
 // word's new match intervals.  The seed map keeps its grown bucket count from word to word (unordered_map::clear), which
 // is the only coupling between words; the words are then independent and run on all host threads.
+//
+// max_seeds > 0 (ref: HASHING/SeedHash.hpp:56-69, 85-93): an oversized bucket is not enumerated itself; its haplotypes go, in
+// bucket order, into a FRESH map keyed by the next word, whose buckets are visited recursively in that map's iteration
+// order.  The rank is then the position of the haplotype's final (nested) bucket in this depth-first visit.
 template <class WordFn>
-std::vector<uint32_t> seedGroupRanks(const uint32_t numHaps, const int numWords, WordFn&& rawWord, const unsigned threads = 0)
+std::vector<uint32_t> seedGroupRanks(const uint32_t numHaps, const int numWords, WordFn&& rawWord, const unsigned threads = 0,
+                                     const int maxSeeds = 0, const int readAhead = 0)
 {
   std::vector<uint32_t> rank(static_cast<size_t>(std::max(numWords, 0)) * numHaps);
   if (numWords <= 0) {
@@ -249,14 +254,52 @@ std::vector<uint32_t> seedGroupRanks(const uint32_t numHaps, const int numWords,
       bool isNew;
       nodeOfHap[h] = seeds.insert(rawWord(h, w), 0, isNew);
     }
-    std::vector<uint32_t> rankOfNode(numHaps, 0);
-    uint32_t r = 0;
-    for (int nd = seeds.first(); nd != NodeOrderMap::kEnd; nd = seeds.next(nd)) {
-      rankOfNode[static_cast<size_t>(nd)] = r++;
-    }
     uint32_t* out = rank.data() + static_cast<size_t>(w) * numHaps;
-    for (uint32_t h = 0; h < numHaps; ++h) {
-      out[h] = rankOfNode[static_cast<size_t>(nodeOfHap[h])];
+    uint32_t r = 0;
+    if (maxSeeds > 0) {
+      // members of every bucket in insertion (= haplotype) order, then the depth-first visit
+      std::vector<std::vector<uint32_t>> members(numHaps);
+      for (uint32_t h = 0; h < numHaps; ++h) {
+        members[static_cast<size_t>(nodeOfHap[h])].push_back(h);
+      }
+      const int readWords = std::min(numWords, w + readAhead);
+      struct Visit {
+        static void run(const std::vector<uint32_t>& bucket, const int level, const int readWords, const int maxSeeds,
+                        WordFn& rawWord, uint32_t* out, uint32_t& r)
+        {
+          if (bucket.size() > static_cast<size_t>(maxSeeds) && level + 1 < readWords) {
+            NodeOrderMap sub;
+            std::vector<std::vector<uint32_t>> subMembers;
+            for (const uint32_t h : bucket) {
+              bool isNew;
+              const int nd = sub.insert(rawWord(h, level + 1), 0, isNew);
+              if (static_cast<size_t>(nd) >= subMembers.size()) {
+                subMembers.resize(static_cast<size_t>(nd) + 1);
+              }
+              subMembers[static_cast<size_t>(nd)].push_back(h);
+            }
+            for (int nd = sub.first(); nd != NodeOrderMap::kEnd; nd = sub.next(nd)) {
+              run(subMembers[static_cast<size_t>(nd)], level + 1, readWords, maxSeeds, rawWord, out, r);
+            }
+            return;
+          }
+          for (const uint32_t h : bucket) {
+            out[h] = r;
+          }
+          ++r;
+        }
+      };
+      for (int nd = seeds.first(); nd != NodeOrderMap::kEnd; nd = seeds.next(nd)) {
+        Visit::run(members[static_cast<size_t>(nd)], w, readWords, maxSeeds, rawWord, out, r);
+      }
+    } else {
+      std::vector<uint32_t> rankOfNode(numHaps, 0);
+      for (int nd = seeds.first(); nd != NodeOrderMap::kEnd; nd = seeds.next(nd)) {
+        rankOfNode[static_cast<size_t>(nd)] = r++;
+      }
+      for (uint32_t h = 0; h < numHaps; ++h) {
+        out[h] = rankOfNode[static_cast<size_t>(nodeOfHap[h])];
+      }
     }
   });
   return rank;

@@ -26,6 +26,7 @@
 // reference's hash-map iteration order).
 #pragma once
 
+#include <climits>
 #include <cstdint>
 #include <cuda_runtime.h>
 
@@ -68,6 +69,10 @@ struct SeedArgs {
   fsmc_match* out;
   long long capacity;
   const unsigned char* lowComplexity;  // [W] 1 = low-complexity word (DecodingParams::skip), nullptr = none
+  // max_seeds > 0 (nestedKeysKernels below): haps / keysT hold REGISTRATION keys instead of the haplotype words, and a
+  // registration at word x moves the interval's end to x + depth (bits 32.. of the key), at most maxDepth words ahead
+  int nested;
+  int maxDepth;
 };
 
 // The tables of word j of the batch.
@@ -213,6 +218,145 @@ __global__ void groupScatterKernel(const SeedArgs args)
   }
 }
 
+// -------------------------------------------------------------------------------------------------------------------
+// max_seeds (ref: HASHING/SeedHash.hpp:56-69, 85-93): a bucket of word c with more than max_seeds haplotypes is not
+// enumerated; its members are re-hashed on word c+1 (recursively, while the next word is inside the read-ahead buffer:
+// c+j+1 < min(W, c + readAhead)), and the pairs of the final, nested bucket are extended to word c+j, not c.  Order-free
+// form: every (word c, haplotype h) gets a REGISTRATION KEY = (depth j, representative haplotype of the nested bucket at
+// that depth).  Two haplotypes are paired by the reference at word c iff their registration keys at c are equal, and
+// the pair's interval end moves to c + j.  With these keys in place of the words, grouping, start test and extension
+// are the kernels of the plain case.
+//
+// Level 0 groups word c by the word itself (groupInsertKernel) and records each haplotype's representative rep0[c][h]
+// (the slot owner: unique per distinct word).  Level j >= 1 groups the haplotypes of word c that are not final yet by the
+// exact 64-bit key (representative at level j-1, rep0[c+j][h]).
+// -------------------------------------------------------------------------------------------------------------------
+struct NestArgs {
+  uint32_t H;
+  int W;
+  uint32_t C;
+  int maxSeeds, readAhead;
+  int level;
+  int wordBase;             // first word of the batch; blockIdx.y = word within the batch
+  uint32_t* owner;          // [batch][C]
+  uint32_t* slotCount;      // [batch][C]
+  uint32_t* slotOf;         // [batch][H]
+  uint32_t* rep0;           // [W][H]
+  uint32_t* cur;            // [W][H] representative at the current depth
+  unsigned char* depth;     // [W][H] bit 7 = final
+  unsigned long long* pending;  // number of (word, haplotype) entries that go one level deeper
+  uint64_t* regKeyT;        // [W][H]
+};
+
+__device__ __forceinline__ bool nestGoesDeeper(const NestArgs& a, const uint32_t n, const int w, const int level)
+{
+  const int readWords = min(a.W, w + a.readAhead);  // ref: FastSMC.cpp:188-199 (GLOBAL_READ_WORDS while word w is current)
+  return n > static_cast<uint32_t>(a.maxSeeds) && w + level + 1 < readWords;
+}
+
+// after groupInsertKernel on the raw words of the batch
+__global__ void nestLevel0Kernel(const NestArgs a)
+{
+  const int w = a.wordBase + static_cast<int>(blockIdx.y);
+  const size_t j = blockIdx.y;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
+    const uint32_t s = a.slotOf[j * a.H + h];
+    const uint32_t rep = a.owner[j * a.C + s] - 1u;
+    const bool deeper = nestGoesDeeper(a, a.slotCount[j * a.C + s], w, 0);
+    const size_t o = static_cast<size_t>(w) * a.H + h;
+    a.rep0[o] = rep;
+    a.cur[o] = rep;
+    a.depth[o] = deeper ? 0 : 0x80;
+    if (deeper) {
+      atomicAdd(a.pending, 1ull);
+    }
+  }
+}
+
+__device__ __forceinline__ uint64_t nestKey(const NestArgs& a, const int w, const uint32_t h)
+{
+  return (static_cast<uint64_t>(a.cur[static_cast<size_t>(w) * a.H + h]) << 32) |
+         a.rep0[static_cast<size_t>(w + a.level) * a.H + h];
+}
+
+__global__ void nestInsertKernel(const NestArgs a)
+{
+  const int w = a.wordBase + static_cast<int>(blockIdx.y);
+  const size_t j = blockIdx.y;
+  uint32_t* owner = a.owner + j * a.C;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
+    if (a.depth[static_cast<size_t>(w) * a.H + h] & 0x80) {
+      continue;
+    }
+    const uint64_t k = nestKey(a, w, h);
+    uint32_t slot = mixKey(k) & (a.C - 1);
+    for (;;) {
+      uint32_t o = owner[slot];
+      if (o == 0) {
+        o = atomicCAS(&owner[slot], 0u, h + 1u);
+        if (o == 0) {
+          o = h + 1u;
+        }
+      }
+      if (o == h + 1u || nestKey(a, w, o - 1u) == k) {
+        break;
+      }
+      slot = (slot + 1u) & (a.C - 1);
+    }
+    a.slotOf[j * a.H + h] = slot;
+    atomicAdd(&a.slotCount[j * a.C + slot], 1u);
+  }
+}
+
+// reads owner / slotCount only (no haplotype's `cur` is read here, so they can be updated in place)
+__global__ void nestFinishKernel(const NestArgs a)
+{
+  const int w = a.wordBase + static_cast<int>(blockIdx.y);
+  const size_t j = blockIdx.y;
+  for (uint32_t h = blockIdx.x * blockDim.x + threadIdx.x; h < a.H; h += gridDim.x * blockDim.x) {
+    const size_t o = static_cast<size_t>(w) * a.H + h;
+    if (a.depth[o] & 0x80) {
+      continue;
+    }
+    const uint32_t s = a.slotOf[j * a.H + h];
+    const bool deeper = nestGoesDeeper(a, a.slotCount[j * a.C + s], w, a.level);
+    a.cur[o] = a.owner[j * a.C + s] - 1u;
+    a.depth[o] = static_cast<unsigned char>(a.level | (deeper ? 0 : 0x80));
+    if (deeper) {
+      atomicAdd(a.pending, 1ull);
+    }
+  }
+}
+
+__global__ void nestEmitKernel(const NestArgs a)
+{
+  const size_t total = static_cast<size_t>(a.W) * a.H;
+  for (size_t o = blockIdx.x * static_cast<size_t>(blockDim.x) + threadIdx.x; o < total; o += static_cast<size_t>(gridDim.x) * blockDim.x) {
+    a.regKeyT[o] = (static_cast<uint64_t>(a.depth[o] & 0x7f) << 32) | a.cur[o];
+  }
+}
+
+// [W][H] -> [H][W] (the walks of pairExtendKernel read one haplotype's consecutive words)
+__global__ void transposeKeysBackKernel(const uint64_t* __restrict__ keysT, const uint32_t H, const int W, uint64_t* __restrict__ keys)
+{
+  __shared__ uint64_t tile[32][33];
+  const uint32_t h0 = blockIdx.x * 32u;
+  const int w0 = blockIdx.y * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int w = w0 + r;
+    const uint32_t h = h0 + threadIdx.x;
+    tile[r][threadIdx.x] = (h < H && w < W) ? keysT[static_cast<size_t>(w) * H + h] : 0ull;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const uint32_t h = h0 + r;
+    const int w = w0 + threadIdx.x;
+    if (h < H && w < W) {
+      keys[static_cast<size_t>(h) * W + w] = tile[threadIdx.x][r];
+    }
+  }
+}
+
 constexpr int kPairChunk = 8;        // consecutive pair indices per thread
 constexpr int kLaneWords = 8;        // words a lane extends its own interval before the warp takes over
 constexpr int kPairBlockThreads = 256;
@@ -249,7 +393,15 @@ __device__ __forceinline__ bool pairInJob(const SeedArgs& a, const uint32_t hi, 
   return false;
 }
 
-__global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const SeedArgs args)
+// NESTED (max_seeds > 0): A/B rows hold registration keys; a registration at word x proposes the end x + depth(key).
+// The reference's bookkeeping per pair (ExtendHash.hpp:61-106): a registration sets end = max(end, x + depth); a
+// low-complexity word sets end = x for whatever is alive; after a seeded word c an interval with end < c - gap is flushed.
+__device__ __forceinline__ int keyDepth(const uint64_t k)
+{
+  return static_cast<int>(k >> 32);
+}
+
+template <bool NESTED> __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const SeedArgs args)
 {
   const unsigned lane = threadIdx.x & 31u;
   __shared__ unsigned long long blockChunk;
@@ -324,18 +476,46 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
           isStart = true;
           const uint64_t* A = a.haps + static_cast<size_t>(hLo) * a.wordsPerHap;
           const uint64_t* B = a.haps + static_cast<size_t>(hHi) * a.wordsPerHap;
-          // alive before w?  Walk back: gap+1 misses in a row mean the earlier interval was flushed; a low-complexity
-          // word extends whatever is alive without being a match itself, so it restarts the count of misses
-          // (ref: ExtendHash.hpp:85-106)
-          int missesBack = 0;
-          for (int x = w - 1; x >= 0 && missesBack <= a.gap; --x) {
-            if (a.lowComplexity && a.lowComplexity[x]) {
-              missesBack = 0;
-            } else if (__ldg(A + x) == __ldg(B + x)) {
-              isStart = false;
-              break;
-            } else {
-              ++missesBack;
+          if constexpr (!NESTED) {
+            // alive before w?  Walk back: gap+1 misses in a row mean the earlier interval was flushed; a low-complexity
+            // word extends whatever is alive without being a match itself, so it restarts the count of misses
+            // (ref: ExtendHash.hpp:85-106)
+            int missesBack = 0;
+            for (int x = w - 1; x >= 0 && missesBack <= a.gap; --x) {
+              if (a.lowComplexity && a.lowComplexity[x]) {
+                missesBack = 0;
+              } else if (__ldg(A + x) == __ldg(B + x)) {
+                isStart = false;
+                break;
+              } else {
+                ++missesBack;
+              }
+            }
+          } else {
+            // The same question when ends run ahead of the registrations.  Walking back, `need` is the smallest end an
+            // interval must have after word x to be alive before w (kAny: being alive is enough): a seeded word x without
+            // a sufficient registration raises it to x - gap; a low-complexity word resets every end to x, so it either
+            // satisfies the need (alive before it is then enough) or rules the past out.  Nothing before x can help
+            // once need > x - 1 + maxDepth.
+            constexpr int kAny = INT_MIN;
+            int need = kAny;
+            for (int x = w - 1; x >= 0; --x) {
+              if (a.lowComplexity && a.lowComplexity[x]) {
+                if (x >= need) {
+                  need = kAny;
+                  continue;
+                }
+                break;
+              }
+              const uint64_t ka = __ldg(A + x);
+              if (ka == __ldg(B + x) && x + keyDepth(ka) >= need) {
+                isStart = false;
+                break;
+              }
+              need = max(need, x - a.gap);
+              if (need > x - 1 + a.maxDepth) {
+                break;
+              }
             }
           }
         }
@@ -359,12 +539,29 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
       if (isStart) {
         const uint64_t* A = a.haps + static_cast<size_t>(hLo) * a.wordsPerHap;
         const uint64_t* B = a.haps + static_cast<size_t>(hHi) * a.wordsPerHap;
+        if constexpr (NESTED) {
+          end = w + keyDepth(__ldg(A + w));
+        }
         for (int k = 0; k < kLaneWords && open && pos < a.W; ++k, ++pos) {
-          if ((a.lowComplexity && a.lowComplexity[pos]) || __ldg(A + pos) == __ldg(B + pos)) {
-            end = pos;
-            misses = 0;
-          } else if (++misses > a.gap) {
-            open = false;
+          if constexpr (!NESTED) {
+            if ((a.lowComplexity && a.lowComplexity[pos]) || __ldg(A + pos) == __ldg(B + pos)) {
+              end = pos;
+              misses = 0;
+            } else if (++misses > a.gap) {
+              open = false;
+            }
+          } else {
+            if (a.lowComplexity && a.lowComplexity[pos]) {
+              end = pos;
+            } else {
+              const uint64_t ka = __ldg(A + pos);
+              if (ka == __ldg(B + pos)) {
+                end = max(end, pos + keyDepth(ka));
+              }
+              if (end < pos - a.gap) {
+                open = false;
+              }
+            }
           }
         }
         if (pos >= a.W) {
@@ -383,16 +580,43 @@ __global__ void __launch_bounds__(kPairBlockThreads) pairExtendKernel(const Seed
         bool sOpen = true;
         for (int p0 = sPos; p0 < a.W && sOpen; p0 += 32) {
           const int x = p0 + static_cast<int>(lane);
-          const bool eq = x < a.W && ((a.lowComplexity && a.lowComplexity[x]) || __ldg(A + x) == __ldg(B + x));
-          const unsigned m = __ballot_sync(0xffffffffu, eq);
           const int valid = min(32, a.W - p0);
-          for (int b = 0; b < valid; ++b) {  // warp-uniform walk over the 32 comparison bits
-            if ((m >> b) & 1u) {
-              sEnd = p0 + b;
-              sMisses = 0;
-            } else if (++sMisses > a.gap) {
-              sOpen = false;
-              break;
+          if constexpr (!NESTED) {
+            const bool eq = x < a.W && ((a.lowComplexity && a.lowComplexity[x]) || __ldg(A + x) == __ldg(B + x));
+            const unsigned m = __ballot_sync(0xffffffffu, eq);
+            for (int b = 0; b < valid; ++b) {  // warp-uniform walk over the 32 comparison bits
+              if ((m >> b) & 1u) {
+                sEnd = p0 + b;
+                sMisses = 0;
+              } else if (++sMisses > a.gap) {
+                sOpen = false;
+                break;
+              }
+            }
+          } else {
+            // per word: -1 = nothing, -2 = low-complexity word, else the end a registration proposes
+            int ev = -1;
+            if (x < a.W) {
+              if (a.lowComplexity && a.lowComplexity[x]) {
+                ev = -2;
+              } else {
+                const uint64_t ka = __ldg(A + x);
+                if (ka == __ldg(B + x)) {
+                  ev = x + keyDepth(ka);
+                }
+              }
+            }
+            for (int b = 0; b < valid; ++b) {
+              const int e = __shfl_sync(0xffffffffu, ev, b);
+              if (e == -2) {
+                sEnd = p0 + b;
+                continue;
+              }
+              sEnd = max(sEnd, e);
+              if (sEnd < p0 + b - a.gap) {
+                sOpen = false;
+                break;
+              }
             }
           }
         }

@@ -257,6 +257,12 @@ typedef struct fsmc_seed_params {
    * haplotype words divided by numHaps is <= skip is "low complexity": no pair is seeded at it, and every interval that is
    * alive there is extended to it.  0 = off (every word has at least one distinct value).                              */
   float skip;
+  /* DecodingParams::max_seeds (HASHING/SeedHash.hpp:56-69, 85-93): a bucket of more than maxSeeds identical words is not
+   * enumerated; its haplotypes are re-hashed on the next word (recursively, while that word lies inside the reference's
+   * read-ahead buffer of readAhead = DecodingParams::constReadAhead words), and the pairs of the final nested bucket are
+   * extended to the deepest word.  0 = off.                                                                              */
+  int32_t maxSeeds;
+  int32_t readAhead;
 } fsmc_seed_params;
 
 typedef struct fsmc_seed_stats {

@@ -395,3 +395,59 @@ def test_low_complexity_word_skipping_equals_oracle(asmc, oracle_mod, tmp_path, 
     else:
         key = lambda a: np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))
         assert np.array_equal(got[key(got)], want[key(want)])  # the same candidate multiset
+
+
+@pytest.mark.parametrize("options", [dict(max_seeds=20), dict(max_seeds=50, gap=2, min_m=2.5), dict(max_seeds=8, gap=0, min_m=1.0),
+                                     dict(max_seeds=8, skip=0.13), dict(max_seeds=3)],
+                         ids=["max_seeds20", "max_seeds50-gap2", "max_seeds8-gap0", "max_seeds8-skip0.13", "max_seeds3"])
+@pytest.mark.parametrize("reference_order", [True, False], ids=["reference-order", "canonical-order"])
+def test_sub_hashing_of_oversized_buckets_equals_oracle(asmc, oracle_mod, tmp_path, options, reference_order):
+    """DecodingParams::max_seeds (SeedHash.hpp:56-69, 85-93): a bucket with more than max_seeds haplotypes is re-hashed on
+    the following words (inside the read-ahead buffer) and its pairs are extended to the deepest word.  Dense synthetic
+    data (6 founders: buckets of ~60 haplotypes), so nearly every word sub-hashes, several levels deep.  Candidate stream
+    bit-exact against the oracle (which equals the reference build with these options, tests/test_reference_build.py);
+    in exact mode and reference order the .ibd.gz is identical too."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, 200, 1920, 3000 * 1920, 1, 11, founders=6)
+    options = dict(dict(min_m=2.0), **options)
+    o = oracle_mod.Oracle(root, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, **dict(REGRESSION_PARAMS, **options))
+    want = o.seed().astype(np.int64)
+    plain = oracle_mod.Oracle(root, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o0"), hashing=True,
+                              **dict(REGRESSION_PARAMS, **dict(options, max_seeds=0))).seed().astype(np.int64)
+    if options["max_seeds"] <= 20:
+        assert len(want) != len(plain) or not np.array_equal(want, plain)  # the option changes the candidates on this data
+    p = _synthetic_params(asmc, root, str(tmp_path / "gpu"), FASTSMC_EXAMPLE_DQ, exactArithmetic=True,
+                          referenceCandidateOrder=reference_order, **options)
+    f = asmc.FastSMC(p)
+    f.setKeepCandidates(True)
+    f.run()
+    got = f.getCandidates().astype(np.int64)
+    assert len(want) > 300 and len(got) == len(want)
+    key = lambda a: np.lexsort((a[:, 3], a[:, 2], a[:, 1], a[:, 0]))
+    assert np.array_equal(got[key(got)], want[key(want)])  # the same candidate multiset
+    if reference_order:
+        assert np.array_equal(got, want)
+        ref_path = str(tmp_path / "oracle.ibd.gz")
+        n = o.run(ref_path)
+        mine = _lines(f"{p.outFileRoot}.1.1.FastSMC.ibd.gz")
+        assert len(mine) == n and mine == _lines(ref_path)
+
+
+@pytest.mark.parametrize("max_seeds", [50, 500])
+def test_sub_hashing_at_larger_buckets(asmc, oracle_mod, tmp_path, max_seeds):
+    """max_seeds in {50, 500} on 4 000 haplotypes drawn from 6 founders (buckets of several hundred haplotypes, i.e. above
+    both cut-offs): the candidate stream in reference order equals the oracle's."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, 2000, 1280, 3000 * 1280, 1, 5, founders=6)
+    options = dict(min_m=2.0, max_seeds=max_seeds)
+    o = oracle_mod.Oracle(root, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, **dict(REGRESSION_PARAMS, **options))
+    want = o.seed().astype(np.int64)
+    p = _synthetic_params(asmc, root, str(tmp_path / "gpu"), FASTSMC_EXAMPLE_DQ, **options)
+    f = asmc.FastSMC(p)
+    f.setKeepCandidates(True)
+    f.run()
+    got = f.getCandidates().astype(np.int64)
+    assert len(want) > 1000 and len(got) == len(want)
+    assert np.array_equal(got, want)
