@@ -130,6 +130,7 @@ struct fsmc_ctx {
   // coefficients 0: alpha stays 0 there, so every posterior is unchanged).  kernelModel = model when S is 69 or 159.
   fsmc::DeviceModel kernelModel{};
   DevBuf<float> kernelSiteRows;
+  DevBuf<float> laneAux;  // kernelModel.laneAux
   DevBuf<float> siteRows, prior, expTimes, colRatios;
   DevBuf<uint64_t> haps;
   long long numHaps = 0;
@@ -295,7 +296,14 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bo
   const int pref = (flags & FSMC_ONE_WARP_KERNEL) ? 0 : splitPreference();
   const bool trySplit = pref == 1 || (pref == -1 && S == 159);
   if (trySplit && (S == 69 || S == 159) && m.stateThreshold <= 32) {
-    fsmc::SplitChoice sc = S == 69 ? fsmc::splitKernel69(rqWanted, acc) : fsmc::splitKernel159(rqWanted, acc);
+    fsmc::SplitChoice sc{};
+    static const bool laneOff = [] { const char* e = std::getenv("FSMC_LANE"); return e && *e == '0'; }();  // A/B runs
+    if (S == 159 && narrow && m.laneAux && !laneOff) {
+      sc = fsmc::laneKernel159(rqWanted);  // states cut across the lanes of a warp (decode_lane.cuh)
+    }
+    if (!sc.fn) {
+      sc = S == 69 ? fsmc::splitKernel69(rqWanted, acc) : fsmc::splitKernel159(rqWanted, acc);
+    }
     if (!sc.fn && narrow) {
       sc = S == 69 ? fsmc::splitKernel69(0, acc) : fsmc::splitKernel159(0, acc);  // no such record width: full rows
     }
@@ -563,6 +571,15 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
     ctx->kernelModel.S = Sk;
     ctx->kernelModel.Spad = SpadK;
     ctx->kernelModel.siteRows = ctx->kernelSiteRows.p;
+  }
+  ctx->model.laneAux = nullptr;
+  ctx->kernelModel.laneAux = nullptr;
+  if (ctx->kernelModel.S == 159) {
+    FSMC_CUDA(ctx->laneAux.ensure(static_cast<size_t>(L) * fsmc::laneAuxFloats159()));
+    fsmc::buildLaneAux159(L, ctx->kernelModel.siteRows, ctx->laneAux.p, blocks, st);
+    FSMC_CUDA(cudaGetLastError());
+    FSMC_CUDA(cudaStreamSynchronize(st));
+    ctx->kernelModel.laneAux = ctx->laneAux.p;
   }
   ctx->hasModel = true;
   return FSMC_OK;

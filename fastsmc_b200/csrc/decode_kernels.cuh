@@ -35,7 +35,8 @@ struct DeviceModel {
   int S;       // states
   int Spad;    // S rounded up to a multiple of 4 (float4 loads)
   int L;       // sites
-  const float* siteRows;   // [L][7][Spad]
+  const float* siteRows;   // [L][kRowArrays][Spad]
+  const float* laneAux;    // [L][Spad + 16] suffix products of RR inside the state quarters (decode_lane.cuh); 159-state models only
   const float* prior;      // [Spad] initialStateProb
   const float* expTimes;   // [Spad] expectedTimes
   const float* colRatios;  // [Spad] columnRatios

@@ -25,4 +25,10 @@ struct SplitChoice {
 SplitChoice splitKernel69(int recordQuads, bool acc);
 SplitChoice splitKernel159(int recordQuads, bool acc);
 
+// Lane-split kernel (decode_lane.cuh, lane_159.cu): FastSMC_exe's default flags at 159 states, records of 1 or 2 quads.
+// It reads the per-site laneAux table of the model (buildLaneAux159).
+SplitChoice laneKernel159(int recordQuads);
+size_t laneAuxFloats159();
+void buildLaneAux159(int L, const float* rows, float* aux, int blocks, cudaStream_t st);
+
 }  // namespace fsmc
