@@ -298,7 +298,7 @@ FastChoice chooseFastKernel(const DeviceModel& m, const unsigned flags, const bo
   if (trySplit && (S == 69 || S == 159) && m.stateThreshold <= 32) {
     fsmc::SplitChoice sc{};
     static const bool laneOff = [] { const char* e = std::getenv("FSMC_LANE"); return e && *e == '0'; }();  // A/B runs
-    if (S == 159 && narrow && m.laneAux && !laneOff) {
+    if (S == 159 && m.laneAux && !laneOff) {
       sc = fsmc::laneKernel159(rqWanted);  // states cut across the lanes of a warp (decode_lane.cuh)
     }
     if (!sc.fn) {

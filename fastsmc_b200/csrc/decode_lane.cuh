@@ -601,3 +601,356 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
 }
 
 }  // namespace fsmc
+
+namespace fsmc
+{
+
+// -------------------------------------------------------------------------------------------------------------------
+// decodeLaneWideKernel: the same lane-split sweeps when every state reaches the consumers (per-site posterior mean / MAP,
+// per-segment age estimates over all states: `noConditionalAgeEstimates`).  Full beta rows stream through HBM: a lane
+// writes its own 40 states per site ([pos][state quad][pair in tile][4]: the 8 lanes of a quarter write 128 contiguous
+// bytes) and reads them back in the forward sweep into the registers of the dead alpha(p-1).  The posterior's
+// normaliser, mean and argmax are reduced across the four quarters with shuffles; every lane of a pair runs the
+// run-length state machine of the segment caller on the same numbers, quarter 0 emits.  The per-state sums of a run
+// (FSMC_SEG_AGE) live in shared memory, [state][pair in tile] — emitSegment's layout — and are touched only while a
+// pair of the warp is inside a run.
+// -------------------------------------------------------------------------------------------------------------------
+template <int S_T, int G, int DEPTH> struct LaneWideSmem {
+  using Base = LaneSmem<S_T, 1, G, DEPTH>;
+  using Geo = LaneGeom<S_T>;
+  static constexpr size_t kExpOff = Base::kTotal;                                     // expected times [Spad]
+  static constexpr size_t kAccOff = (kExpOff + static_cast<size_t>(Geo::Spad) * 4 + 127) / 128 * 128;  // [Spad][32]
+  static constexpr size_t kTotal = kAccOff + static_cast<size_t>(Geo::Spad) * 32 * 4;
+};
+
+template <int S_T, int G, int DEPTH, int MIN_BLOCKS>
+__global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneWideKernel(const __grid_constant__ FastModel fm,
+                                                                                     const __grid_constant__ DecodeArgs args)
+{
+  using Geo = LaneGeom<S_T>;
+  using SM = LaneSmem<S_T, 1, G, DEPTH>;
+  using SMW = LaneWideSmem<S_T, G, DEPTH>;
+  constexpr int S = S_T, Spad = Geo::Spad, SEG = Geo::SEG, SEGQ = Geo::SEGQ, SQ = Geo::SQ;
+  constexpr size_t kRowFloats = static_cast<size_t>(kRowArrays) * Spad;
+  constexpr size_t kAuxFloats = Geo::kAuxFloats;
+  constexpr uint32_t kCoefBytes = static_cast<uint32_t>(SM::kCoefBytes), kAuxBytes = static_cast<uint32_t>(SM::kAuxBytes);
+  static_assert(G % 2 == 0, "the two state vectors swap roles every step");
+
+  extern __shared__ __align__(128) unsigned char smemRaw[];
+  const DeviceModel& m = fm.base;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 3, pl = lane & 7;
+  const int K0 = g * SEG;
+  float* sCr = reinterpret_cast<float*>(smemRaw + SM::kConstOff);
+  float* sCpre = sCr + Spad;
+  float* sPrior = sCpre + Spad;
+  float* sCq = sPrior + Spad;
+  float* sExp = reinterpret_cast<float*>(smemRaw + SMW::kExpOff);
+  float* sAcc = reinterpret_cast<float*>(smemRaw + SMW::kAccOff);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smemRaw + SM::kBarOff);
+  volatile long long* tileSlot = reinterpret_cast<volatile long long*>(smemRaw + SM::kTileOff);
+  auto coefArea = [&](const int slot) { return reinterpret_cast<float*>(smemRaw + static_cast<size_t>(slot) * SM::kSlotBytes); };
+  auto auxArea = [&](const int slot) {
+    return reinterpret_cast<float*>(smemRaw + static_cast<size_t>(slot) * SM::kSlotBytes + static_cast<size_t>(G) * kCoefBytes);
+  };
+  const bool leader = threadIdx.x == 0;
+  for (int k = threadIdx.x; k < Spad; k += blockDim.x) {
+    sCr[k] = k < S ? fm.colRatios[k < S ? k : 0] : 0.f;
+    sPrior[k] = k < S ? fm.prior[k < S ? k : 0] : 0.f;
+    sExp[k] = k < S ? fm.expTimes[k < S ? k : 0] : 0.f;
+  }
+  if (leader) {
+    for (int i = 0; i < DEPTH; ++i) {
+      mbarInit(&bars[i], 1);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  if (threadIdx.x < kLaneQuarters) {
+    float c = 1.f;
+    for (int i = 0; i < SEG; ++i) {
+      sCpre[threadIdx.x * SEG + i] = c;
+      c *= sCr[threadIdx.x * SEG + i];
+    }
+    sCq[threadIdx.x] = c;
+  }
+  __syncthreads();
+  uint32_t parity = 0;
+
+  const unsigned flags = args.flags;
+  const bool wantSeg = flags & FSMC_CALL_SEGMENTS;
+  const bool wantAge = (flags & FSMC_SEG_AGE) && wantSeg;
+  const bool wantSite = flags & (FSMC_SITE_MEAN | FSMC_SITE_MAP);
+  const int sT = m.stateThreshold;
+  const int nAcc = m.ageThreshold;
+  float4* slab = reinterpret_cast<float4*>(args.scratch + static_cast<long long>(blockIdx.x) * args.scratchPerWarp);
+
+  for (long long it = 0;; ++it) {
+    if (leader) {
+      tileSlot[it & 1] = static_cast<long long>(atomicAdd(args.tileCounter, 1ull));
+    }
+    __syncthreads();
+    const long long t = tileSlot[it & 1];
+    if (t >= args.numTiles) {
+      break;
+    }
+    const int tile = args.order ? args.order[t] : static_cast<int>(t);
+    const int nPairs = args.tilePairs[tile];
+    const int from = args.tileFrom[tile];
+    const int len = args.tileTo[tile] - from;
+    const int scanFrom = wantSeg ? args.tileScanFrom[tile] : 0;
+    const int scanTo = wantSeg ? args.tileScanTo[tile] : 0;
+    const int pairInTile = warp * 8 + pl;
+    const bool laneActive = pairInTile < nPairs;
+    const int srcPair = laneActive ? pairInTile : nPairs - 1;
+    const uint32_t pair = static_cast<uint32_t>(tile) * 32u + static_cast<uint32_t>(pairInTile);
+    PairBits bits;
+    bits.a = m.haps + static_cast<size_t>(args.hapA[static_cast<size_t>(tile) * 32 + srcPair]) * m.wordsPerHap;
+    bits.b = m.haps + static_cast<size_t>(args.hapB[static_cast<size_t>(tile) * 32 + srcPair]) * m.wordsPerHap;
+    const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowFloats;
+    const float* auxBase = fm.base.laneAux + static_cast<size_t>(from) * kAuxFloats;
+    // this lane's part of the beta row of window position p: quads [g SEGQ, (g+1) SEGQ) of [p][quad][pair in tile]
+    auto betaAt = [&](const int p, const int q) { return slab + (static_cast<size_t>(p) * SQ + g * SEGQ + q) * 32 + pairInTile; };
+    auto storeBeta = [&](const float (&v)[SEG], const int p) {
+#pragma unroll
+      for (int q = 0; q < SEGQ; ++q) {
+        *betaAt(p, q) = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+      }
+    };
+    float* accCol = sAcc + static_cast<size_t>(K0) * 32 + pairInTile;  // [state K0 + i][pair]: entry i at accCol[i * 32]
+
+    float a[SEG], c[SEG];
+    if (wantAge) {
+#pragma unroll
+      for (int i = 0; i < SEG; ++i) {
+        accCol[i * 32] = 0.f;
+      }
+    }
+
+    // ---- sweep 1: backward ---------------------------------------------------------------------------------------------
+    {
+      const int steps = len - 1;
+      const int nGroups = (steps + G - 1) / G;
+      auto prefetch = [&](const int gi) {
+        const int j0 = gi * G, j1 = min(steps, j0 + G);
+        const int slot = gi % DEPTH;
+        const uint32_t n = static_cast<uint32_t>(j1 - j0);
+        mbarExpectTx(&bars[slot], n * (kCoefBytes + kAuxBytes));
+        bulkLoad(coefArea(slot), rowBase + static_cast<size_t>(len - j1) * kRowFloats, n * kCoefBytes, &bars[slot]);
+        bulkLoad(auxArea(slot), auxBase + static_cast<size_t>(len - j1) * kAuxFloats, n * kAuxBytes, &bars[slot]);
+      };
+      if (leader) {
+        for (int gi = 0; gi < DEPTH && gi < nGroups; ++gi) {
+          prefetch(gi);
+        }
+      }
+#pragma unroll
+      for (int i = 0; i < SEG; ++i) {
+        a[i] = K0 + i < S ? 1.f : 0.f;
+      }
+      storeBeta(a, len - 1);
+      for (int gi = 0; gi < nGroups; ++gi) {
+        const int slot = gi % DEPTH;
+        const int j0 = gi * G;
+        const int n = min(G, steps - j0);
+        const float* coef = coefArea(slot);
+        const float* aux = auxArea(slot);
+        mbarWait(&bars[slot], (parity >> slot) & 1u);
+        parity ^= 1u << slot;
+        auto step = [&](const int i, float (&x)[SEG], float (&y)[SEG]) {
+          const int p = len - 2 - (j0 + i);
+          const int cls = bits.cls(from + p + 1);
+          backwardLane<S>(x, y, coef + static_cast<size_t>(n - 1 - i) * kRowFloats, aux + static_cast<size_t>(n - 1 - i) * kAuxFloats,
+                          cls, g, pl);
+          if (i == G - 1) {
+            scaleLane<SEG>(y, 1.0f / sumLane<SEG>(y));
+          }
+          storeBeta(y, p);
+        };
+#pragma unroll 1
+        for (int i = 0; i < G; i += 2) {
+          if (i < n) {
+            step(i, a, c);
+          }
+          if (i + 1 < n) {
+            step(i + 1, c, a);
+          }
+        }
+        __syncthreads();
+        if (leader && gi + DEPTH < nGroups) {
+          prefetch(gi + DEPTH);
+        }
+      }
+    }
+
+    // ---- sweep 2: forward + fused consumers (ref: HMM.cpp:725-879, 669-692, 1179-1357, 1378-1409) ------------------------
+    {
+      const int nGroups = (len + G - 1) / G;
+      auto prefetch = [&](const int gi) {
+        const int p0 = gi * G;
+        const uint32_t n = static_cast<uint32_t>(min(G, len - p0));
+        const int slot = gi % DEPTH;
+        mbarExpectTx(&bars[slot], n * (kCoefBytes + kAuxBytes));
+        bulkLoad(coefArea(slot), rowBase + static_cast<size_t>(p0) * kRowFloats, n * kCoefBytes, &bars[slot]);
+        bulkLoad(auxArea(slot), auxBase + static_cast<size_t>(p0) * kAuxFloats, n * kAuxBytes, &bars[slot]);
+      };
+      if (leader) {
+        for (int gi = 0; gi < DEPTH && gi < nGroups; ++gi) {
+          prefetch(gi);
+        }
+      }
+      CallerState cs;
+
+      // consumers of window position p: v = alpha(p) (this lane's states); w = the dead vector, receives beta, then alpha*beta
+      auto consume = [&](const int p, const float (&v)[SEG], float (&w)[SEG]) {
+        const int site = from + p;
+        float2 z01 = pk(0.f, 0.f), z23 = pk(0.f, 0.f);
+#pragma unroll
+        for (int q = 0; q < SEGQ; ++q) {
+          const float4 b4 = *betaAt(p, q);
+          const float2 lo = __fmul2_rn(pk(v[4 * q], v[4 * q + 1]), pk(b4.x, b4.y));
+          const float2 hi = __fmul2_rn(pk(v[4 * q + 2], v[4 * q + 3]), pk(b4.z, b4.w));
+          w[4 * q] = lo.x;
+          w[4 * q + 1] = lo.y;
+          w[4 * q + 2] = hi.x;
+          w[4 * q + 3] = hi.y;
+          z01 = __fadd2_rn(z01, lo);
+          z23 = __fadd2_rn(z23, hi);
+        }
+        float z = (z01.x + z01.y) + (z23.x + z23.y);
+        z += __shfl_xor_sync(kFull, z, 8);
+        z += __shfl_xor_sync(kFull, z, 16);
+        const float r = 1.0f / z;  // ref HMM.cpp:681-685
+        const bool inScan = wantSeg && site >= scanFrom && site < scanTo;
+        const bool wantIbd = (flags & FSMC_SITE_IBD) || inScan;
+        if (wantSite) {
+          float mean = 0.f, best = 0.f;
+          int arg = K0;
+#pragma unroll
+          for (int i = 0; i < SEG; ++i) {
+            mean = fmaf(w[i], sExp[K0 + i], mean);
+            if (best < w[i]) {  // first maximum, as the reference's ascending scan
+              best = w[i];
+              arg = K0 + i;
+            }
+          }
+#pragma unroll
+          for (int d = 8; d <= 16; d <<= 1) {
+            mean += __shfl_xor_sync(kFull, mean, d);
+            const float ob = __shfl_xor_sync(kFull, best, d);
+            const int oa = __shfl_xor_sync(kFull, arg, d);
+            if (ob > best || (ob == best && oa < arg)) {
+              best = ob;
+              arg = oa;
+            }
+          }
+          if (g == 0 && laneActive) {
+            if (flags & FSMC_SITE_MEAN) {
+              args.siteMean[static_cast<size_t>(pair) * args.siteStride + p] = mean * r;
+            }
+            if (flags & FSMC_SITE_MAP) {
+              args.siteMap[static_cast<size_t>(pair) * args.siteStride + p] = best > 0.f ? arg : 0;
+            }
+          }
+        }
+        if (wantIbd) {
+          float ibdRaw = 0.f;
+          forStatesBelow<SEG>(sT, [&](const int k) { ibdRaw += w[k]; });  // meaningful in quarter 0 (sT <= SEG)
+          const float ibd = __shfl_sync(kFull, ibdRaw, pl) * r;
+          if ((flags & FSMC_SITE_IBD) && g == 0 && laneActive) {
+            args.siteIbd[static_cast<size_t>(pair) * args.siteStride + p] = ibd;
+          }
+          if (inScan) {
+            // every lane of a pair runs the same run-length state machine on the same numbers; quarter 0 emits
+            int now = ibd >= m.thr[0] ? 0 : (ibd >= m.thr[1] ? 1 : (ibd >= m.thr[2] ? 2 : (ibd >= m.thr[3] ? 3 : -1)));
+            if (!laneActive) {
+              now = -1;
+            }
+            const bool changed = now != cs.level;
+            const bool ending = changed && cs.level >= 0;  // the run that ended at site-1 is written now
+            const bool closing = now >= 0 && site == scanTo - 1;
+            if (__any_sync(kFull, ending)) {
+              __syncwarp();  // the sums of the four quarters are in shared memory
+              if (g == 0 && ending) {
+                emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, sAcc + pairInTile, wantAge);
+              }
+              __syncwarp();
+            }
+            if (wantAge && __any_sync(kFull, now >= 0 || changed)) {
+              // per-state sums of the current run (ref: HMM.cpp:1209-1218,1229,1257,1284,1311)
+              if (now >= 0 || changed) {
+                const float rr = now >= 0 ? r : 0.f;
+                const float keep = changed ? 0.f : 1.f;
+#pragma unroll
+                for (int i = 0; i < SEG; ++i) {
+                  if (K0 + i < nAcc) {
+                    accCol[i * 32] = fmaf(w[i], rr, keep * accCol[i * 32]);
+                  }
+                }
+              }
+            }
+            if (__any_sync(kFull, closing)) {
+              __syncwarp();
+              if (g == 0 && closing) {
+                emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now,
+                                   sAcc + pairInTile, wantAge);
+              }
+              __syncwarp();
+            }
+            cs.prob = (now >= 0 && !closing) ? (changed ? ibd : cs.prob + ibd) : 0.f;
+            cs.start = (now >= 0 && changed) ? site : cs.start;
+            cs.level = now;
+          }
+        }
+      };
+
+      for (int gi = 0; gi < nGroups; ++gi) {
+        const int slot = gi % DEPTH;
+        const int p0 = gi * G;
+        const int n = min(G, len - p0);
+        const float* coef = coefArea(slot);
+        mbarWait(&bars[slot], (parity >> slot) & 1u);
+        parity ^= 1u << slot;
+        auto step = [&](const int i, float (&x)[SEG], float (&y)[SEG]) {
+          const int p = p0 + i;
+          const int cls = bits.cls(from + p);
+          const float total = forwardLane<S>(x, y, coef + static_cast<size_t>(i) * kRowFloats, cls, sCr, sCpre, sCq, g, pl);
+          if (i == G - 1) {
+            scaleLane<SEG>(y, 1.0f / total);
+          }
+          consume(p, y, x);
+        };
+#pragma unroll 1
+        for (int i = 0; i < G; i += 2) {
+          if (i == 0 && gi == 0) {
+            // p = 0: alpha(from)[k] = prior[k] * emission  (ref HMM.cpp:736-743)
+            const int cls = bits.cls(from);
+            const float4* E = reinterpret_cast<const float4*>(coef + cls * Spad) + g * SEGQ;
+            const float4* P = reinterpret_cast<const float4*>(sPrior) + g * SEGQ;
+#pragma unroll
+            for (int q = 0; q < SEGQ; ++q) {
+              const float4 e4 = E[q], p4 = P[q];
+              const float2 lo = __fmul2_rn(pk(p4.x, p4.y), pk(e4.x, e4.y)), hi = __fmul2_rn(pk(p4.z, p4.w), pk(e4.z, e4.w));
+              a[4 * q] = lo.x;
+              a[4 * q + 1] = lo.y;
+              a[4 * q + 2] = hi.x;
+              a[4 * q + 3] = hi.y;
+            }
+            consume(0, a, c);
+          } else if (i < n) {
+            step(i, c, a);
+          }
+          if (i + 1 < n) {
+            step(i + 1, a, c);
+          }
+        }
+        __syncthreads();
+        if (leader && gi + DEPTH < nGroups) {
+          prefetch(gi + DEPTH);
+        }
+      }
+    }
+  }
+}
+
+}  // namespace fsmc

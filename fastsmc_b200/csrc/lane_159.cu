@@ -15,10 +15,18 @@ template <int S, int RQ, int MINB> static SplitChoice makeLane()
                      LaneSmem<S, RQ, kLaneGroup, kLaneDepth>::kTotal, RQ, LaneGeom<S>::Spad, false};
 }
 
+template <int S, int MINB> static SplitChoice makeLaneWide()
+{
+  return SplitChoice{decodeLaneWideKernel<S, kLaneGroup, kLaneDepth, MINB>, kLaneQuarters,
+                     LaneWideSmem<S, kLaneGroup, kLaneDepth>::kTotal, 0, LaneGeom<S>::Spad, true};
+}
+
 SplitChoice laneKernel159(const int recordQuads)
 {
   static const bool four = [] { const char* e = std::getenv("FSMC_LANE"); return e && *e == '4'; }();  // A/B: 4 CTAs per SM (spills)
   switch (recordQuads) {
+  case 0:
+    return makeLaneWide<159, 3>();  // every state reaches the consumers: full beta rows through HBM
   case 1:
     return four ? makeLane<159, 1, 4>() : makeLane<159, 1, 3>();
   case 2:

@@ -25,7 +25,8 @@ struct SplitChoice {
 SplitChoice splitKernel69(int recordQuads, bool acc);
 SplitChoice splitKernel159(int recordQuads, bool acc);
 
-// Lane-split kernel (decode_lane.cuh, lane_159.cu): FastSMC_exe's default flags at 159 states, records of 1 or 2 quads.
+// Lane-split kernels (decode_lane.cuh, lane_159.cu) at 159 states: records of 1 or 2 quads (FastSMC_exe's default flags),
+// or recordQuads = 0: full beta rows (per-site mean / MAP, age estimates over all states).
 // It reads the per-site laneAux table of the model (buildLaneAux159).
 SplitChoice laneKernel159(int recordQuads);
 size_t laneAuxFloats159();
