@@ -37,9 +37,9 @@ DQ_159 = os.path.join(ROOT, "tests", "golden", "fastsmc_example", "example.decod
 FLOPS_PER_PAIR_SITE_STATE = 35  # 15 forward + 15 backward + 3 combine + 2 consume
 NCU_NARROW_DRAM_BYTES_PER_PAIR_SITE = (6.072805e9 + 6.078759e9) / (37888 * 10000)  # profiles/r1_v4_decodeNarrow_s69_ncu_full.txt
 NCU_DRAM_BYTES_PER_PAIR_SITE = (109.922461e9 + 109.458343e9) / (37888 * 10000)  # profiles/r1_v4_decodeFast_s69_ncu_full.txt
-# profiles/r2_final_decodeNarrowSparse_ncu_full.txt: 86.44 GB read + 100.90 GB written by one launch of decodeNarrowKernel<69, sparse>
+# profiles/r2_p2_decodeNarrowSparse_ncu_full.txt: 87.83 GB read + 101.53 GB written by one launch of decodeNarrowKernel<69, sparse>
 # over cfg2 (blocks of 128 sites); refineKernel adds 75.8 GB per step (profiles/r2_final_refine_ncu_full.txt)
-NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE = (86.442088e9 + 100.896670e9) / (499500 * 10000)
+NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE = (87.827249e9 + 101.530119e9) / (499500 * 10000)
 WORKLOAD = "cfg2: all-pairs, hashing off, 1000 haplotypes x 10000 SNPs, S=69 (30-100-2000), time=50, batchSize=32"
 
 
@@ -447,7 +447,7 @@ def main():
         ln.close()
 
     # ---- cfg2 repeated with the 159-state table of FASTSMC_EXAMPLE, rank 0's first 2 048 batches,
-    # both flag sets: the state-split kernels (decode_split.cuh) -----------------------------------------------------------
+    # both flag sets: the lane-split kernels (decode_lane.cuh) ------------------------------------------------------------
     states159 = None
     if rank == 0 and not args.no_states159:
         p.decodingQuantFile = DQ_159
@@ -477,8 +477,9 @@ def main():
             r159 = pl.collect()
             tf = sub_pair_sites / (ms / 1e3) * FLOPS_PER_PAIR_SITE_STATE * S159 / 1e12
             states159[label] = {"value": sub_pair_sites / (ms / 1e3), "unit": "pair-sites/s", "ms_per_step": ms,
-                                "kernel": f"decodeSplitKernel<{int(r159.stats.statesKernel)}, {int(r159.stats.tileWarps)} warps, "
-                                          f"{'narrow' if r159.stats.narrowKernel else 'wide'}>",
+                                "kernel": (f"decodeLaneKernel<{int(r159.stats.statesKernel)}, records>" if r159.stats.narrowKernel
+                                           else f"decodeLaneWideKernel<{int(r159.stats.statesKernel)}>") + " (states cut across the lanes of a warp, "
+                                          "8 pairs per warp, one 32-pair tile per CTA)",
                                 "fp32_tflops": tf, "fp32_frac_nominal": tf / (torch.cuda.get_device_properties(local).multi_processor_count * 128 * 2 * 1.965e9 / 1e12)}
             pl.close()
             c159.close()
@@ -533,7 +534,7 @@ def main():
             bytes_per_pair_site = 0.25 + 32.0 + 4.0 * ((S + 3) // 4 * 4) / sparse["block_sites"]
             kernel_name = "decodeNarrowKernel<69, sparse> (+ refineKernel<69>, finalizeSegmentsKernel: ~6 % of the step)"
             ncu_bytes = NCU_SPARSE_DRAM_BYTES_PER_PAIR_SITE
-            traffic_src = "ncu --set full capture of the kernel in this bench (profiles/r2_final_decodeNarrowSparse_ncu_full.txt), scaled by pair-sites"
+            traffic_src = "ncu --set full capture of the kernel in this bench (profiles/r2_p2_decodeNarrowSparse_ncu_full.txt), scaled by pair-sites"
         else:
             # the backward sweep writes beta[S] floats and the forward sweep reads them back (8*S) + 2 genotype bits
             bytes_per_pair_site = 8.0 * S + 0.25

@@ -217,7 +217,8 @@ int fsmc_plan_destroy(fsmc_ctx* ctx, fsmc_plan* plan);
  * match interval [startWord, endWord] of a pair a < b starts at a matching word with no match in
  * the preceding gap+1 words, and is extended while the next match is at most gap+1 words ahead
  * (low-complexity words, see fsmc_seed_params.skip, count as neither match nor miss for an open interval
- * and move its end).
+ * and move its end; with fsmc_seed_params.maxSeeds a "match" at w is membership of the same nested bucket and moves the
+ * interval's end up to readAhead-1 words past w, see there).
  * Intervals are produced for pairs that pass the job filter on GLOBAL haplotype ids
  * (HASHING/SeedHash.hpp:99-129) and, unless FSMC_SEED_ALL_INTERVALS is set, whose genetic length
  * 100*(gen[min(64*end+63, L-1)] - gen[64*start]) is >= minLengthCm.

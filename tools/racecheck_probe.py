@@ -48,8 +48,8 @@ def main():
     for label, r, dq, conditional, env in (
             ("wide69", root, DQ69, False, {}), ("narrow69", root, DQ69, True, {}),
             ("split-wide69", root, DQ69, False, {"FSMC_SPLIT": "1"}), ("split-narrow69", root, DQ69, True, {"FSMC_SPLIT": "1"}),
-            ("split-wide159", EX, EX + ".decodingQuantities.gz", False, {}),
-            ("split-narrow159", EX, EX + ".decodingQuantities.gz", True, {})):
+            ("lane-wide159", EX, EX + ".decodingQuantities.gz", False, {}),
+            ("lane-narrow159", EX, EX + ".decodingQuantities.gz", True, {})):
         for k, v in env.items():
             os.environ[k] = v
         ctx, data = context(r, dq, conditional)
