@@ -9,6 +9,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <map>
+#include <tuple>
 #include <numeric>
 #include <string>
 #include <thread>
@@ -167,6 +169,9 @@ struct fsmc_ctx {
   // a destroyed plan is parked here so that the next fsmc_plan_create reuses its device buffers (fsmc_decode makes
   // one plan per call; cudaMalloc/cudaFree per call would serialise the device)
   fsmc_plan* sparePlan = nullptr;
+  // (kernel, threads, dynamic shared memory) -> resident CTAs per SM: the attribute / occupancy queries of a plan are made
+  // once per context, not once per call (they and cudaMemGetInfo were 10-90 ms of a 300 ms fsmc_decode call)
+  std::map<std::tuple<const void*, int, size_t>, int> occupancy;
 };
 
 struct fsmc_plan {
@@ -626,6 +631,29 @@ int fsmc_query_kernel(fsmc_ctx* ctx, const uint32_t flags, const double meanScan
   return FSMC_OK;
 }
 
+namespace
+{
+// cudaFuncSetAttribute(max dynamic shared memory) + resident CTAs per SM, cached per context
+cudaError_t residentBlocks(fsmc_ctx* ctx, const void* fn, const int threads, const size_t smem, int* blocksPerSm)
+{
+  const auto key = std::make_tuple(fn, threads, smem);
+  const auto it = ctx->occupancy.find(key);
+  if (it != ctx->occupancy.end()) {
+    *blocksPerSm = it->second;
+    return cudaSuccess;
+  }
+  cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem));
+  if (e != cudaSuccess) {
+    return e;
+  }
+  e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(blocksPerSm, fn, threads, smem);
+  if (e == cudaSuccess) {
+    ctx->occupancy[key] = *blocksPerSm;
+  }
+  return e;
+}
+}  // namespace
+
 int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** out)
 {
   if (!ctx || !req || !out) {
@@ -635,6 +663,15 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   if (!ctx->hasModel || !ctx->hasHaps) {
     return fail(FSMC_E_STATE, "fsmc_plan_create: set the model and the haplotypes first");
   }
+  static const bool tracePlan = std::getenv("FSMC_TRACE_PLAN") != nullptr;  // development: host time of the phases below
+  auto tMark = std::chrono::steady_clock::now();
+  auto mark = [&](const char* what) {
+    if (tracePlan) {
+      const auto now = std::chrono::steady_clock::now();
+      std::fprintf(stderr, "  plan_create %s %.2f ms\n", what, std::chrono::duration<double, std::milli>(now - tMark).count());
+      tMark = now;
+    }
+  };
   const long long T = req->numTiles;
   if (T < 0 || T > (1ll << 26)) {
     return fail(FSMC_E_INVALID, "fsmc_plan_create: numTiles=%lld out of range", T);
@@ -712,6 +749,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     return (req->tileTo[x] - req->tileFrom[x]) > (req->tileTo[y] - req->tileFrom[y]);
   });
 
+  mark("validate + order");
   cudaStream_t st = ctx->stream;
   const size_t nLane = static_cast<size_t>(T) * 32;
   FSMC_CUDA(plan->hapA.ensure(nLane));
@@ -756,6 +794,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   }
   plan->launched = false;
   plan->launches = 0;
+  mark("buffers + uploads");
 
   // ---- launch geometry --------------------------------------------------------------------------
   const KernelChoice kc = chooseKernel(m.S, flags);
@@ -777,8 +816,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   if (plan->fast) {
     plan->threads = fc.threads;
     plan->smemBytes = fastSmemBytes(fc, ctx->kernelModel.S);
-    FSMC_CUDA(cudaFuncSetAttribute(fc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
-    FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, fc.fn, plan->threads, plan->smemBytes));
+    FSMC_CUDA(residentBlocks(ctx, reinterpret_cast<const void*>(fc.fn), plan->threads, plan->smemBytes, &blocksPerSm));
   } else {
     const size_t perWarp = smemPerWarp(m, kc.mode, flags);
     while (warpsPerBlock > 1 && perWarp * warpsPerBlock > smemLimit) {
@@ -790,8 +828,7 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     }
     plan->threads = warpsPerBlock * 32;
     plan->smemBytes = perWarp * warpsPerBlock;
-    FSMC_CUDA(cudaFuncSetAttribute(kc.fn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->smemBytes)));
-    FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&blocksPerSm, kc.fn, plan->threads, plan->smemBytes));
+    FSMC_CUDA(residentBlocks(ctx, reinterpret_cast<const void*>(kc.fn), plan->threads, plan->smemBytes, &blocksPerSm));
   }
   if (blocksPerSm < 1) {
     return fail(FSMC_E_CUDA, "fsmc_plan_create: kernel does not fit on an SM (threads=%d smem=%zu)", plan->threads,
@@ -812,7 +849,8 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
   // the slabs would not fit in 85% of the free memory.
   plan->scratchPerWarp = maxLen * (plan->fast ? (fc.narrow ? fc.recordQuads * 4 : fc.Spad) : m.S) * 32;
   const size_t slabBytes = static_cast<size_t>(plan->scratchPerWarp) * sizeof(float);
-  if (slabBytes > 0) {
+  // (the context's buffer already holds the full grid's slabs: nothing to size, no driver query)
+  if (slabBytes > 0 && ctx->scratch.n < static_cast<size_t>(blocks) * warpsPerBlock * static_cast<size_t>(plan->scratchPerWarp)) {
     size_t freeB = 0, totalB = 0;
     FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
     const size_t have = ctx->scratch.n * sizeof(float);
@@ -831,13 +869,27 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
 
   plan->blocks = static_cast<int>(blocks);
   plan->tilesPerBlock = warpsPerBlock;
+  mark("geometry + scratch");
 
   if (plan->sparse) {
     // ---- checkpoints, items and the refine pass (decode_sparse.cuh) -------------------------------------------------
     const size_t vecFloats = static_cast<size_t>(fc.Spad) * 32;
-    size_t freeB = 0, totalB = 0;
-    FSMC_CUDA(cudaMemGetInfo(&freeB, &totalB));
-    const double budget = 0.45 * static_cast<double>(freeB + ctx->ckptBeta.n * sizeof(float));
+    // budget for the checkpoints: 45 % of what is free, or what the context already holds if that is more (then the
+    // driver is not asked at all: cudaMemGetInfo costs milliseconds)
+    double budget = static_cast<double>(ctx->ckptBeta.n * sizeof(float));
+    bool asked = false;
+    auto askBudget = [&]() -> cudaError_t {
+      if (!asked) {
+        size_t freeB = 0, totalB = 0;
+        const cudaError_t e = cudaMemGetInfo(&freeB, &totalB);
+        if (e != cudaSuccess) {
+          return e;
+        }
+        budget = std::max(budget, 0.45 * static_cast<double>(freeB + ctx->ckptBeta.n * sizeof(float)));
+        asked = true;
+      }
+      return cudaSuccess;
+    };
     // blocks of 128 sites (measured on cfg2: 385 ms per step with blocks of 32 sites, 340 ms with 128: every block boundary
     // inside an IBD run costs the warp an item, and every block a checkpoint); coarser when the checkpoints of the whole
     // request would not fit
@@ -855,6 +907,10 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
       base[T] = slots;
       if (static_cast<double>(slots) * vecFloats * sizeof(float) <= budget || shift >= 12) {
         break;
+      }
+      if (!asked) {
+        FSMC_CUDA(askBudget());
+        --shift;  // try the same block size again with the real budget
       }
     }
     plan->ckptShift = shift;
@@ -879,15 +935,15 @@ int fsmc_plan_create(fsmc_ctx* ctx, const fsmc_decode_request* req, fsmc_plan** 
     auto refineFn = fsmc::refineKernel<69, fsmc::kRefineDepth, kFastRescale, 128, 2>;
     plan->refineSmem = 4 * (fsmc::kRefineDepth * (vecFloats * 4 + static_cast<size_t>(fsmc::kRowArrays) * fc.Spad * 4)) +
                        4 * 2 * fsmc::kRefineDepth * sizeof(uint64_t);
-    FSMC_CUDA(cudaFuncSetAttribute(refineFn, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(plan->refineSmem)));
     int perSm = 0;
-    FSMC_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSm, refineFn, 128, plan->refineSmem));
+    FSMC_CUDA(residentBlocks(ctx, reinterpret_cast<const void*>(refineFn), 128, plan->refineSmem, &perSm));
     if (perSm < 1) {
       return fail(FSMC_E_CUDA, "fsmc_plan_create: refine kernel does not fit on an SM (smem=%zu)", plan->refineSmem);
     }
     plan->refineBlocks = ctx->prop.multiProcessorCount * perSm;
     const size_t refineScratch = static_cast<size_t>(plan->refineBlocks) * 4 * (size_t{1} << shift) * vecFloats;
     FSMC_CUDA(ctx->scratch.ensure(std::max<size_t>(refineScratch, static_cast<size_t>(blocks) * static_cast<size_t>(warpsPerBlock) * static_cast<size_t>(plan->scratchPerWarp))));
+    mark("sparse buffers");
   }
   guard.keep = true;
   *out = plan;

@@ -266,6 +266,26 @@ template <int SEG> __device__ __forceinline__ void scaleLane(float (&a)[SEG], co
   }
 }
 
+// PairBits with the haplotype indices instead of row pointers (registers limit this kernel's occupancy)
+struct LaneBits {
+  uint32_t ha, hb;
+  uint64_t x = 0, t = 0;
+  int word = -1;
+  __device__ __forceinline__ int cls(const DeviceModel& m, const int site)
+  {
+    const int w = site >> 6;
+    if (w != word) {
+      const uint64_t wa = __ldg(m.haps + static_cast<size_t>(ha) * m.wordsPerHap + w);
+      const uint64_t wb = __ldg(m.haps + static_cast<size_t>(hb) * m.wordsPerHap + w);
+      x = wa ^ wb;
+      t = wa & wb;
+      word = w;
+    }
+    const int bit = site & 63;
+    return ((x >> bit) & 1ull) ? 1 : (((t >> bit) & 1ull) ? 2 : 0);
+  }
+};
+
 template <int S_T, int RQ, int G, int DEPTH, int MIN_BLOCKS>
 __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKernel(const __grid_constant__ FastModel fm,
                                                                                  const __grid_constant__ DecodeArgs args)
@@ -345,19 +365,20 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
     const bool laneActive = pairInTile < nPairs;
     const int srcPair = laneActive ? pairInTile : nPairs - 1;
     const uint32_t pair = static_cast<uint32_t>(tile) * 32u + static_cast<uint32_t>(pairInTile);
-    PairBits bits;
-    bits.a = m.haps + static_cast<size_t>(args.hapA[static_cast<size_t>(tile) * 32 + srcPair]) * m.wordsPerHap;
-    bits.b = m.haps + static_cast<size_t>(args.hapB[static_cast<size_t>(tile) * 32 + srcPair]) * m.wordsPerHap;
-    const float* rowBase = m.siteRows + static_cast<size_t>(from) * kRowFloats;
-    const float* auxBase = fm.base.laneAux + static_cast<size_t>(from) * kAuxFloats;
+    LaneBits bits;
+    bits.ha = args.hapA[static_cast<size_t>(tile) * 32 + srcPair];
+    bits.hb = args.hapB[static_cast<size_t>(tile) * 32 + srcPair];
     // record of window position p, quad q of this lane's pair: [p][q][pair in tile]
     auto recAt = [&](const int p, const int q) { return slab + (static_cast<size_t>(p) * RQ + q) * 32 + pairInTile; };
 
     float a[SEG], c[SEG];
-    float acc[NR];
+    // per-state sums of the lane's current run: in this lane's column of the warp's parking area (emitSegment reads them
+    // there with a stride of 32 floats); registers are what limits this kernel's occupancy
+    if (g == 0) {
 #pragma unroll
-    for (int k = 0; k < NR; ++k) {
-      acc[k] = 0.f;
+      for (int k = 0; k < NR; ++k) {
+        park[k * 32] = 0.f;
+      }
     }
     // (beta^[k < sT], 0.., scale divisor) of window position p: quarter-0 lanes only
     auto storeRecord = [&](const float (&v)[SEG], const int p, const float divisor) {
@@ -384,8 +405,8 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
         const int slot = gi % DEPTH;
         const uint32_t n = static_cast<uint32_t>(j1 - j0);
         mbarExpectTx(&bars[slot], n * (kCoefBytes + kAuxBytes));
-        bulkLoad(coefArea(slot), rowBase + static_cast<size_t>(len - j1) * kRowFloats, n * kCoefBytes, &bars[slot]);
-        bulkLoad(auxArea(slot), auxBase + static_cast<size_t>(len - j1) * kAuxFloats, n * kAuxBytes, &bars[slot]);
+        bulkLoad(coefArea(slot), m.siteRows + static_cast<size_t>(from + len - j1) * kRowFloats, n * kCoefBytes, &bars[slot]);
+        bulkLoad(auxArea(slot), m.laneAux + static_cast<size_t>(from + len - j1) * kAuxFloats, n * kAuxBytes, &bars[slot]);
       };
       if (leader) {
         for (int gi = 0; gi < DEPTH && gi < nGroups; ++gi) {
@@ -407,7 +428,7 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
         parity ^= 1u << slot;
         auto step = [&](const int i, float (&x)[SEG], float (&y)[SEG]) {
           const int p = len - 2 - (j0 + i);
-          const int cls = bits.cls(from + p + 1);
+          const int cls = bits.cls(m, from + p + 1);
           backwardLane<S>(x, y, coef + static_cast<size_t>(n - 1 - i) * kRowFloats, aux + static_cast<size_t>(n - 1 - i) * kAuxFloats,
                           cls, g, pl);
           float divisor = 1.0f;
@@ -447,8 +468,8 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
         const uint32_t n = static_cast<uint32_t>(min(G, len - p0));
         const int slot = gi % DEPTH;
         mbarExpectTx(&bars[slot], n * (kCoefBytes + kAuxBytes));
-        bulkLoad(coefArea(slot), rowBase + static_cast<size_t>(p0) * kRowFloats, n * kCoefBytes, &bars[slot]);
-        bulkLoad(auxArea(slot), auxBase + static_cast<size_t>(p0) * kAuxFloats, n * kAuxBytes, &bars[slot]);
+        bulkLoad(coefArea(slot), m.siteRows + static_cast<size_t>(from + p0) * kRowFloats, n * kCoefBytes, &bars[slot]);
+        bulkLoad(auxArea(slot), m.laneAux + static_cast<size_t>(from + p0) * kAuxFloats, n * kAuxBytes, &bars[slot]);
       };
       if (leader) {
         for (int gi = 0; gi < DEPTH && gi < nGroups; ++gi) {
@@ -493,33 +514,18 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
           const bool closing = now >= 0 && site == scanTo - 1;
           const float rr = now >= 0 ? r : 0.f;
           const float keep = changed ? 0.f : 1.f;
-          if (ending || closing) {
-            // rare: a run ends at site-1 and/or the scan window closes on a live run.  The per-state sums go through this
-            // lane's column of the warp's parking area (emitSegment reads them with a stride of 32 floats)
-            if (wantAge) {
-#pragma unroll
-              for (int k = 0; k < NR; ++k) {
-                park[k * 32] = acc[k];
-              }
-            }
-            if (ending) {
-              emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, park, wantAge);
-            }
-            if (wantAge) {
-#pragma unroll
-              for (int k = 0; k < NR; ++k) {
-                acc[k] = fmaf(q[k], rr, keep * acc[k]);
-                park[k * 32] = acc[k];
-              }
-            }
-            if (closing) {
-              emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, park, wantAge);
-            }
-          } else if (wantAge) {
+          if (ending) {
+            emitSegment<false>(m, args, pair, cs.start, site - 1, cs.prob, cs.level, park, wantAge);
+          }
+          if (wantAge && (now >= 0 || changed)) {
+            // per-state sums of the current run (ref: HMM.cpp:1209-1218); a run that just ended leaves zeros
 #pragma unroll
             for (int k = 0; k < NR; ++k) {
-              acc[k] = fmaf(q[k], rr, keep * acc[k]);
+              park[k * 32] = fmaf(q[k], rr, keep * park[k * 32]);
             }
+          }
+          if (closing) {
+            emitSegment<false>(m, args, pair, changed ? site : cs.start, site, changed ? ibd : cs.prob + ibd, now, park, wantAge);
           }
           cs.prob = (now >= 0 && !closing) ? (changed ? ibd : cs.prob + ibd) : 0.f;
           cs.start = (now >= 0 && changed) ? site : cs.start;
@@ -536,7 +542,7 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
         parity ^= 1u << slot;
         auto step = [&](const int i, float (&x)[SEG], float (&y)[SEG]) {
           const int p = p0 + i;
-          const int cls = bits.cls(from + p);
+          const int cls = bits.cls(m, from + p);
           float4 rec[RQ];  // this position's record: in flight while the step is computed
 #pragma unroll
           for (int qq = 0; qq < RQ; ++qq) {
@@ -557,7 +563,7 @@ __global__ void __launch_bounds__(kLaneQuarters * 32, MIN_BLOCKS) decodeLaneKern
         for (int i = 0; i < G; i += 2) {
           if (i == 0 && gi == 0) {
             // p = 0: alpha^(0) = prior * emission into a; the one exact normaliser Z_0 = sum_k alpha^(0)[k] beta^(0)[k]
-            const int cls = bits.cls(from);
+            const int cls = bits.cls(m, from);
             float4 rec[RQ];
 #pragma unroll
             for (int qq = 0; qq < RQ; ++qq) {

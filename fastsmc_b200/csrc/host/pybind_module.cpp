@@ -425,18 +425,18 @@ PYBIND11_MODULE(pyASMC, m)
       "data"_a, "params"_a);
   m.def(
       "seedGroupRanks",
-      [](const Data& data) {
+      [](const Data& data, const int maxSeeds, const int readAhead) {
         const uint32_t H = static_cast<uint32_t>(data.numLoadedHaplotypes());
         const int W = data.sites / 64;
         auto rawWord = [&](uint32_t h, int w) {
           return data.hapBits[static_cast<size_t>(h) * data.wordsPerHap + w] ^ data.flipMask[w];
         };
-        const std::vector<uint32_t> r = candidate_order::seedGroupRanks(H, W, rawWord);
+        const std::vector<uint32_t> r = candidate_order::seedGroupRanks(H, W, rawWord, 0, maxSeeds, readAhead);
         py::array_t<uint32_t> out({static_cast<py::ssize_t>(W), static_cast<py::ssize_t>(H)});
         std::copy(r.begin(), r.end(), out.mutable_data());
         return out;
       },
-      "data"_a);
+      "data"_a, "max_seeds"_a = 0, "read_ahead"_a = 10);
   m.def(
       "replayReferenceOrder",
       [](py::array_t<int64_t, py::array::c_style | py::array::forcecast> intervals, const Data& data, int gap,

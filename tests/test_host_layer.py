@@ -265,3 +265,45 @@ def test_packed_matrix_cache_equals_text_read(asmc, tmp_path):
     changed_cached = asmc.Data(params(True))
     same(changed_plain, changed_cached)
     assert not np.array_equal(np.array(changed_plain.hapBits), np.array(plain.hapBits))
+
+
+def test_nested_seed_ranks_follow_the_sub_hash_partition(asmc, tmp_path):
+    """max_seeds (SeedHash.hpp:56-69, 85-93): the seed-map rank of a haplotype at word w is the position of its FINAL nested
+    bucket in the depth-first visit of the sub-hashes.  Checked here: two haplotypes share a rank iff a brute-force walk of
+    the nesting rule (bucket larger than max_seeds and next word inside the read-ahead buffer -> split on the next word)
+    puts them in the same final bucket; ranks are dense; without max_seeds the ranks are those of the words alone."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, 60, 1280, 3000 * 1280, 1, 3, founders=4)
+    p = _params(asmc)
+    p.inFileRoot = root
+    d = asmc.Data(p)
+    H, W = d.hapBits.shape[0], d.sites // 64
+    raw = (d.hapBits[:, :W] ^ np.asarray(d.flipMask, dtype=np.uint64)[None, :W])
+    plain = asmc.pyASMC.seedGroupRanks(d)
+    for max_seeds, read_ahead in ((5, 10), (12, 3), (1, 10)):
+        ranks = asmc.pyASMC.seedGroupRanks(d, max_seeds=max_seeds, read_ahead=read_ahead)
+        assert ranks.shape == (W, H)
+        deeper = 0
+        for w in range(W):
+            read_words = min(W, w + read_ahead)
+            final = {}  # haplotype -> key of its final bucket
+            stack = [(w, np.arange(H))]
+            while stack:
+                level, members = stack.pop()
+                for value in np.unique(raw[members, level]):
+                    bucket = members[raw[members, level] == value]
+                    if len(bucket) > max_seeds and level + 1 < read_words:
+                        stack.append((level + 1, bucket))
+                        deeper += 1
+                    else:
+                        for h in bucket:
+                            final[h] = (level, int(bucket[0]))
+            keys = {}
+            for h in range(H):
+                keys.setdefault(final[h], set()).add(int(ranks[w, h]))
+            assert all(len(v) == 1 for v in keys.values())                      # one rank per final bucket
+            assert len({next(iter(v)) for v in keys.values()}) == len(keys)      # different buckets, different ranks
+            assert sorted(set(ranks[w].tolist())) == list(range(len(keys)))     # dense
+        assert deeper > 0
+    assert np.array_equal(asmc.pyASMC.seedGroupRanks(d, max_seeds=H + 1), plain)
