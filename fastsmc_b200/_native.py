@@ -45,6 +45,7 @@ class Model(C.Structure):
         ("D", C.c_void_p), ("B", C.c_void_p), ("U", C.c_void_p), ("RR", C.c_void_p),
         ("distanceRow", C.c_void_p),
         ("stateThreshold", C.c_int32), ("ageThreshold", C.c_int32), ("probabilityThreshold", C.c_float),
+        ("modelTag", C.c_uint64),
     ]
 
 

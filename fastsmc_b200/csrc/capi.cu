@@ -126,6 +126,7 @@ struct fsmc_ctx {
   cudaStream_t stream = nullptr;
   cudaDeviceProp prop{};
   bool hasModel = false, hasHaps = false;
+  uint64_t modelTag = 0;  // fsmc_model::modelTag of the tables on the device (0 = untagged)
   fsmc::DeviceModel model{};
   // The production kernels are specialised for 69 and 159 states.  Any other state count runs on them too: the model is
   // padded to the next specialised count with states that carry no probability (prior, emissions and transition
@@ -496,6 +497,23 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
   FSMC_CUDA(cudaSetDevice(ctx->device));
   const int Spad = (S + 3) / 4 * 4;
   cudaStream_t st = ctx->stream;
+  auto setThresholds = [&](DeviceModel& dm) {
+    dm.stateThreshold = mdl->stateThreshold;
+    dm.ageThreshold = mdl->ageThreshold;
+    // the reference compares against `N * probabilityThreshold` with an int N promoted to float
+    dm.thr[0] = 1000 * mdl->probabilityThreshold;
+    dm.thr[1] = 100 * mdl->probabilityThreshold;
+    dm.thr[2] = 10 * mdl->probabilityThreshold;
+    dm.thr[3] = mdl->probabilityThreshold;
+  };
+  if (mdl->modelTag != 0 && ctx->hasModel && ctx->modelTag == mdl->modelTag && ctx->model.S == S && ctx->model.L == L) {
+    // the same tables as the ones this context holds (the jobs of one data set): keep the device rows
+    setThresholds(ctx->model);
+    setThresholds(ctx->kernelModel);
+    return FSMC_OK;
+  }
+  ctx->hasModel = false;
+  ctx->modelTag = 0;
 
   // staging copies of the caller's tables, gathered into per-site rows on the device.  The staging buffers belong to the
   // context (grow-only): cudaFree synchronises the whole device, which stalls the other host thread of a GPU that runs
@@ -555,13 +573,7 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
   m.prior = ctx->prior.p;
   m.expTimes = ctx->expTimes.p;
   m.colRatios = ctx->colRatios.p;
-  m.stateThreshold = mdl->stateThreshold;
-  m.ageThreshold = mdl->ageThreshold;
-  // the reference compares against `N * probabilityThreshold` with an int N promoted to float
-  m.thr[0] = 1000 * mdl->probabilityThreshold;
-  m.thr[1] = 100 * mdl->probabilityThreshold;
-  m.thr[2] = 10 * mdl->probabilityThreshold;
-  m.thr[3] = mdl->probabilityThreshold;
+  setThresholds(m);
   m.haps = ctx->haps.p;
   m.wordsPerHap = ctx->hasHaps ? (ctx->sites + 63) / 64 : 0;
   ctx->kernelModel = m;
@@ -587,6 +599,7 @@ int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* mdl)
     ctx->kernelModel.laneAux = ctx->laneAux.p;
   }
   ctx->hasModel = true;
+  ctx->modelTag = mdl->modelTag;
   return FSMC_OK;
 }
 

@@ -725,6 +725,18 @@ std::vector<std::vector<int>> Data::calculateUndistinguishedCounts(const int num
   return cache.counts;
 }
 
+std::shared_ptr<const void> Data::sharedObject(const std::string& key,
+                                               const std::function<std::shared_ptr<const void>()>& make) const
+{
+  UndistinguishedCache& cache = *mUndistinguished;
+  std::lock_guard<std::mutex> g(cache.objectsLock);
+  auto it = cache.objects.find(key);
+  if (it == cache.objects.end()) {
+    it = cache.objects.emplace(key, make()).first;
+  }
+  return it->second;
+}
+
 std::vector<std::vector<int>> Data::drawUndistinguishedCounts(const int numCsfsSamples) const
 {
   std::vector<std::vector<int>> counts(sites, std::vector<int>(3, 0));

@@ -10,6 +10,8 @@
 #include <string>
 #include <utility>
 #include <vector>
+#include <map>
+#include <functional>
 
 #include "DecodingParams.hpp"
 
@@ -77,6 +79,10 @@ public:
   /// The Data of job params.jobInd of params.jobs, cut out of `whole` (a Data that loaded every sample, i.e. read
   /// with jobs = jobInd = 1): the same object Data(params) would read from the files, without reading them again.
   static Data forJob(const Data& whole, const DecodingParams& params);
+  /// An object that depends on the WHOLE data set only, not on the job's sample subset (e.g. the emission / transition
+  /// tables of HMM): built once by `make` and shared by the jobs cut out of one data set (forJob), like the
+  /// undistinguished counts.  Builders of the same data set are serialised; `make` may call calculateUndistinguishedCounts.
+  std::shared_ptr<const void> sharedObject(const std::string& key, const std::function<std::shared_ptr<const void>()>& make) const;
 
   /// Packed-matrix cache of a FastSMC-mode data set read with jobs = 1 (DecodingParams::hapBitCache): false when there is
   /// no valid cache for these files and options.
@@ -122,6 +128,9 @@ private:
     int csfsSamples = -1;
     bool knownSeed = false;
     std::vector<std::vector<int>> counts;
+    // further objects that depend on the whole data set only (HMM's model tables): see sharedObject
+    std::mutex objectsLock;
+    std::map<std::string, std::shared_ptr<const void>> objects;
   };
   mutable std::shared_ptr<UndistinguishedCache> mUndistinguished = std::make_shared<UndistinguishedCache>();
   std::vector<std::vector<int>> drawUndistinguishedCounts(int numCsfsSamples) const;

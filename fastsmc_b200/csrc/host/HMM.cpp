@@ -130,7 +130,30 @@ HMM::HMM(Data _data, const DecodingParams& _decodingParams, int /*_scalingSkip*/
   m_batchSize = decodingParams.batchSize;
   sequenceLength = data.sites;
   const double tTables = now();
-  m_model = buildModelTables(data, m_decodingQuant, decodingParams);
+  {
+    // The tables depend on the whole data set (allele counts, positions), the decoding quantities and a few options, not on
+    // the job's sample subset: the jobs cut out of one data set build them once (Data::sharedObject) and pooled device
+    // contexts that already hold them skip the upload (fsmc_model::modelTag).
+    struct SharedModel {
+      ModelTables tables;
+      uint64_t tag = 0;
+    };
+    char opts[96];
+    std::snprintf(opts, sizeof opts, "|%d%d%d%d|%.9g|%d|%d", int(decodingParams.foldData), int(decodingParams.usingCSFS),
+                  int(decodingParams.decodingSequence), int(decodingParams.noConditionalAgeEstimates),
+                  static_cast<double>(decodingParams.skipCSFSdistance), decodingParams.time, int(decodingParams.useKnownSeed));
+    const std::string key = "HMM::ModelTables|" + decodingParams.decodingQuantFile + opts;
+    const std::shared_ptr<const void> obj = data.sharedObject(key, [&]() -> std::shared_ptr<const void> {
+      static std::atomic<uint64_t> nextTag{1};
+      auto sm = std::make_shared<SharedModel>();
+      sm->tables = buildModelTables(data, m_decodingQuant, decodingParams);
+      sm->tag = nextTag++;
+      return sm;
+    });
+    const SharedModel& sm = *static_cast<const SharedModel*>(obj.get());
+    m_model = sm.tables;
+    m_modelTag = sm.tag;
+  }
   m_stats.tablesWallS = now() - tTables;
   stateThreshold = static_cast<unsigned>(m_model.stateThreshold);
   ageThreshold = static_cast<unsigned>(m_model.ageThreshold);
@@ -308,6 +331,7 @@ void HMM::uploadModelTo(fsmc_ctx*& ctx)
   m.stateThreshold = m_model.stateThreshold;
   m.ageThreshold = m_model.ageThreshold;
   m.probabilityThreshold = m_model.probabilityThreshold;
+  m.modelTag = m_modelTag;
   check(fsmc_set_model(m_ctx, &m), "fsmc_set_model");
   check(fsmc_set_haplotypes(m_ctx, data.hapBits.data(), static_cast<int64_t>(data.numLoadedHaplotypes()), data.sites),
         "fsmc_set_haplotypes");

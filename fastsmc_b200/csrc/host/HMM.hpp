@@ -123,6 +123,7 @@ public:
     float probabilityThreshold = 0.f;
   };
   const ModelTables& getModelTables() const { return m_model; }
+  uint64_t m_modelTag = 0;  // identity of m_model among the jobs of one data set (fsmc_model::modelTag)
   /// Host-only part of the constructor (no GPU needed): emission tables incl. the reference's RNG sequence
   /// (ref: HMM.cpp:159-256), per-site transition rows and the IBD thresholds (ref: HMM.cpp:93-105).
   static ModelTables buildModelTables(const Data& data, const DecodingQuantities& dq, const DecodingParams& params);

@@ -74,6 +74,10 @@ typedef struct fsmc_model {
   int32_t stateThreshold;         /* HMM::getStateThreshold   (HMM.cpp:504-513)              */
   int32_t ageThreshold;           /* HMM.cpp:101-105                                         */
   float probabilityThreshold;     /* HMM.cpp:96-99                                           */
+  /* Optional identity of the tables above (0 = none).  A context that already holds a model with the same non-zero tag,
+   * state and site counts keeps its device tables and only takes the three thresholds: the jobs of one data set
+   * (Data.cpp:62-80) share their emission and transition tables, and a pooled context is handed job after job.          */
+  uint64_t modelTag;
 } fsmc_model;
 
 int fsmc_set_model(fsmc_ctx* ctx, const fsmc_model* model);
