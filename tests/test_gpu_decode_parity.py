@@ -324,9 +324,10 @@ def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69, s
 # ---- 159 states (FASTSMC_EXAMPLE table): the state-split kernels are the production path (4 warps per tile) ---------
 
 
-def test_split_kernels_159_states_default_flags(oracle_mod):
-    """FastSMC's default flags on the example data (age estimates conditional on TMRCA < time): the narrow state-split
-    kernel vs the oracle (per-site IBD probability within 1e-4, same segments) and vs the wide state-split kernel."""
+def test_lane_split_kernels_159_states(oracle_mod):
+    """FastSMC's default flags on the example data (age estimates conditional on TMRCA < time) at 159 states: the lane-split
+    kernels (decode_lane.cuh; records, and full beta rows with FSMC_WIDE_KERNEL) vs the oracle: same segments, per-segment
+    values and per-site IBD probability within 1e-4, over ragged windows, a partially filled tile and a one-site window."""
     from fastsmc_b200 import _native as N
     params = dict(REGRESSION_PARAMS, noConditionalAgeEstimates=False)
     o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test159n", hashing=True, **params)
