@@ -451,3 +451,22 @@ def test_sub_hashing_at_larger_buckets(asmc, oracle_mod, tmp_path, max_seeds):
     got = f.getCandidates().astype(np.int64)
     assert len(want) > 1000 and len(got) == len(want)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("jobs,job_ind", [(4, 2), (4, 3), (4, 4)])
+def test_sub_hashing_inside_jobs(asmc, oracle_mod, tmp_path, jobs, job_ind):
+    """max_seeds together with the jobs/jobInd partition (Data.cpp:62-80): the buckets are those of the job's haplotypes,
+    the job filter applies to the pairs of the final nested buckets.  Candidate stream in reference order vs the oracle."""
+    from fastsmc_b200 import synth
+    root = str(tmp_path / "dense")
+    synth.dataset(root, 300, 1920, 3000 * 1920, 1, 23, founders=6)
+    options = dict(min_m=2.0, max_seeds=10, jobs=jobs, jobInd=job_ind)
+    o = oracle_mod.Oracle(root, FASTSMC_EXAMPLE_DQ, str(tmp_path / "o"), hashing=True, **dict(REGRESSION_PARAMS, **options))
+    want = o.seed().astype(np.int64)
+    p = _synthetic_params(asmc, root, str(tmp_path / "gpu"), FASTSMC_EXAMPLE_DQ, **options)
+    f = asmc.FastSMC(p)
+    f.setKeepCandidates(True)
+    f.run()
+    got = f.getCandidates().astype(np.int64)
+    assert len(want) > 100 and len(got) == len(want)
+    assert np.array_equal(got, want)
