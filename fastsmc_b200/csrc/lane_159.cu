@@ -31,6 +31,10 @@ SplitChoice laneKernel159(const int recordQuads)
     return four ? makeLane<159, 1, 4>() : makeLane<159, 1, 3>();
   case 2:
     return four ? makeLane<159, 2, 4>() : makeLane<159, 2, 3>();
+  case 3:
+    return makeLane<159, 3, 3>();  // --time up to 140 generations with the example table
+  case 4:
+    return makeLane<159, 4, 3>();
   default:
     return {};
   }

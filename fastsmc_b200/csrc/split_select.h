@@ -25,7 +25,7 @@ struct SplitChoice {
 SplitChoice splitKernel69(int recordQuads, bool acc);
 SplitChoice splitKernel159(int recordQuads, bool acc);
 
-// Lane-split kernels (decode_lane.cuh, lane_159.cu) at 159 states: records of 1 or 2 quads (FastSMC_exe's default flags),
+// Lane-split kernels (decode_lane.cuh, lane_159.cu) at 159 states: records of 1 to 4 quads (FastSMC_exe's default flags),
 // or recordQuads = 0: full beta rows (per-site mean / MAP, age estimates over all states).
 // It reads the per-site laneAux table of the model (buildLaneAux159).
 SplitChoice laneKernel159(int recordQuads);

@@ -324,14 +324,15 @@ def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69, s
 # ---- 159 states (FASTSMC_EXAMPLE table): the state-split kernels are the production path (4 warps per tile) ---------
 
 
-def test_lane_split_kernels_159_states(oracle_mod):
+@pytest.mark.parametrize("time", [50, 100, 140], ids=["time50-2quads", "time100-3quads", "time140-4quads"])
+def test_lane_split_kernels_159_states(oracle_mod, time):
     """FastSMC's default flags on the example data (age estimates conditional on TMRCA < time) at 159 states: the lane-split
     kernels (decode_lane.cuh; records, and full beta rows with FSMC_WIDE_KERNEL) vs the oracle: same segments, per-segment
     values and per-site IBD probability within 1e-4, over ragged windows, a partially filled tile and a one-site window."""
     from fastsmc_b200 import _native as N
-    params = dict(REGRESSION_PARAMS, noConditionalAgeEstimates=False)
+    params = dict(REGRESSION_PARAMS, noConditionalAgeEstimates=False, time=time)  # records of 2, 3 and 4 quads
     o = oracle_mod.Oracle(FASTSMC_EXAMPLE, FASTSMC_EXAMPLE_DQ, "/tmp/fsmc_test159n", hashing=True, **params)
-    assert o.age_threshold == o.state_threshold
+    assert o.age_threshold == o.state_threshold == time // 10
     n = o.run("/tmp/fsmc_test159n_oracle.ibd.gz")
     ints, floats = o.segments()
     batches = o.batches()
