@@ -43,6 +43,9 @@ rep = {"n_diploid": n_dip, "sites": n_sites, "jobs": jobs, "gpus": gpus, "refere
        "candidates": sum(r.candidates for r in reports), "pair_sites": sum(r.pairSites for r in reports),
        "decode_kernel_ms": sum(r.kernelMs for r in reports), "seed_kernel_ms": sum(r.seedMs for r in reports),
        "job_wall_s": [round(r.wallSeconds, 2) for r in reports], "job_device": [r.device for r in reports],
+       "job_stages_s": [{k: round(getattr(r, k), 3) for k in ("prepareSeconds", "tablesSeconds", "uploadSeconds", "seedSeconds",
+                                                             "orderSeconds", "decodeSeconds", "outputSeconds") if hasattr(r, k)}
+                        for r in reports],
        "busy_s_per_gpu": {d: round(sum(r.wallSeconds for r in reports if r.device == d), 2) for d in range(gpus)}}
 print(json.dumps(rep, indent=1))
 if out_json:
