@@ -201,6 +201,7 @@ def synthetic69(oracle_mod, tmp_path_factory):
     o = oracle_mod.Oracle(root, DQ_69, "/tmp/fsmc_test69", hashing=False, time=50, noConditionalAgeEstimates=True,
                           doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
     ctx = context_from_oracle(o, oracle_mod)
+    o.dataset_root = root  # for tests that open a second oracle on the same files
     return o, ctx
 
 
@@ -294,8 +295,7 @@ def test_narrow_kernel_matches_oracle_and_wide_kernel(oracle_mod, synthetic69, s
     from fastsmc_b200 import _native as N
     o_wide, ctx_wide = synthetic69
     # a second oracle instance with conditional age estimates (ageThreshold == stateThreshold)
-    import glob
-    root = glob.glob("/tmp/pytest-of-*/pytest-*/syn69*/syn.hap.gz")[-1][:-len(".hap.gz")]
+    root = o_wide.dataset_root
     o = oracle_mod.Oracle(root, DQ_69, "/tmp/fsmc_test69n", hashing=False, time=50, noConditionalAgeEstimates=False,
                           doPerPairMAP=True, doPerPairPosteriorMean=True, batchSize=32)
     ctx = context_from_oracle(o, oracle_mod)
